@@ -1,0 +1,136 @@
+/*
+ * kb200.h -- C ABI of libkb200.so: the B200 (sm_100a) implementation of the novel-view synthesis hot path
+ * of pierlj/ken-burns-effect.  This is the drop-in boundary: plain pointers and sizes, an explicit CUDA
+ * stream, no torch types.  Paths below are relative to the reference tree.
+ *
+ * The reference has no FFI of its own for this path: it JIT-compiles CUDA source strings through cupy and
+ * launches them with raw `tensor.data_ptr()` integers (utils/common.py:377-380, :516-521).  Each entry
+ * point here replaces one such launch site (or one torch/numpy/OpenCV stage of the per-frame loop,
+ * utils/common.py:222-260); the Python mirror that binds them with ctypes is
+ * ken_burns_effect_b200/utils/common.py, and INTEGRATION.md shows the stub a reference maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - tensors are fp32, contiguous, laid out as the reference lays them out (NCHW / [B,C,N]) unless a
+ *     parameter says otherwise;
+ *   - one call = enqueue on `stream` only (no allocation, no synchronisation, re-entrant);
+ *   - return value: 0 on success, a cudaError_t (>0) from the launch, or a negative KB_E* argument error;
+ *     kb_last_error() returns a thread-local description of the last failure;
+ *   - focal and baseline are doubles because the reference pastes them as double literals into its
+ *     kernels (utils/common.py:447,470) and parts of the arithmetic are evaluated in fp64 there.
+ */
+#ifndef KB200_H
+#define KB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define KB_EINVAL (-1)   /* bad argument (null pointer, non-positive size, unsupported C) */
+#define KB_ENOSUP (-2)   /* valid request this build does not support */
+
+typedef void *kb_stream_t; /* cudaStream_t */
+
+/* Library identification.  kb_version() = 10000*major + 100*minor + patch. */
+int kb_version(void);
+const char *kb_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+long long kb_launch_count(void);
+
+/* ---- render_pointcloud, utils/common.py:428-686 ------------------------------------------------ */
+
+/* process_shift's tensor half, utils/common.py:104-109: out = clone(xyz); out.xy *= z/(z+1e-7); out += shift.
+ * xyz, out: [B,3,N]; shift: [B,3] (device) */
+int kb_shift_points(const float *xyz, const float *shift, float *out, int B, long N, kb_stream_t stream);
+
+/* kernel_pointrender_updateZee, utils/common.py:434-521.
+ * xyz [B,3,N].  shift_host: optional HOST pointer to 3 floats added to every point inside the kernel after
+ * the process_shift rescale (fuses utils/common.py:104-109; pass NULL for already shifted points).
+ * zee [B,H,W] is (re)initialised to 1e6 by this call (utils/common.py:430) and then min-reduced.
+ * pix_idx: optional [B,N] int32, receives y*W+x of the pixel each point votes for, or -1 (index map). */
+int kb_splat_min(const float *xyz, int B, long N, const float *shift_host, double focal, double baseline,
+                 float *zee, int H, int W, int32_t *pix_idx, kb_stream_t stream);
+
+/* kernel_pointrender_updateDegrid, utils/common.py:524-582, race-free: reads zee_in, writes zee_out
+ * (the reference updates in place while neighbours are being read; see DESIGN.md "degrid"). */
+int kb_degrid(const float *zee_in, float *zee_out, int B, int H, int W, kb_stream_t stream);
+
+/* kernel_pointrender_updateOutput, utils/common.py:585-684.
+ * data [B,C,N]; zee [B,H,W] (degridded); accum [B,H,W,Cp] channels-last, Cp = kb_accum_channels(C),
+ * zero-initialised by this call; channel C holds the weight sum (the reference's appended ones channel,
+ * utils/common.py:429), channels > C are padding. */
+int kb_accum_channels(int C);
+int kb_splat_accum(const float *xyz, const float *data, int B, long N, int C, const float *shift_host,
+                   double focal, double baseline, const float *zee, float *accum, int H, int W,
+                   kb_stream_t stream);
+
+/* utils/common.py:686: render[B,C,H,W] = accum[..., :C] / (accum[..., C] + 1e-7); existing[B,1,H,W] = accum[..., C]. */
+int kb_normalize(const float *accum, int B, int C, int H, int W, float *render, float *existing,
+                 kb_stream_t stream);
+
+/* The whole of render_pointcloud (four launches above).  workspace: kb_render_workspace_bytes() bytes. */
+size_t kb_render_workspace_bytes(int B, int C, int H, int W);
+int kb_render_pointcloud(const float *xyz, const float *data, int B, long N, int C, int W, int H,
+                         double focal, double baseline, float *render, float *existing, void *workspace,
+                         kb_stream_t stream);
+
+/* ---- fill_disocclusion, utils/common.py:833-937 -------------------------------------------------- */
+/* input [B,C,H,W], depth [B,1,H,W] -> output [B,C,H,W] (input with hole pixels, depth<=0, filled). */
+int kb_fill(const float *input, const float *depth, float *output, int B, int C, int H, int W,
+            kb_stream_t stream);
+
+/* ---- spatial_filter on masks, utils/common.py:417-421 as used by pointcloud_inpainting.py:208-209 -- */
+/* out = median5x5(in) for in in {0,1} (reflect padding) == (5x5 box count >= 13). in/out [B,1,H,W]. */
+int kb_median5_binary(const float *in, float *out, int B, int H, int W, kb_stream_t stream);
+
+/* ---- the per-frame loop of process_kenburns, utils/common.py:222-260, fused ---------------------- */
+
+typedef struct kb_pose {
+  float shift[3];   /* tensorShift of process_shift (utils/common.py:98-102), already rounded to fp32 */
+  float _pad;
+  double focal;     /* currentFocal (utils/common.py:225-229) */
+} kb_pose;
+
+typedef struct kb_frame_params {
+  int H, W;              /* render / output frame size (objectCommon intHeight/intWidth) */
+  int crop_w, crop_h;    /* getRectSubPix patch size (utils/common.py:256) */
+  double baseline;       /* objectCommon['dblBaseline'] */
+} kb_frame_params;
+
+#define KB_MAX_POSES 32
+
+/* Bytes of device scratch needed to render K poses at once. */
+size_t kb_frames_workspace_bytes(const kb_frame_params *p, int K);
+
+/* Renders K (<= KB_MAX_POSES) frames of one point cloud in one call: for each pose
+ *   process_shift -> render_pointcloud(C=4: RGB+depth) -> fill_disocclusion -> *255/clip/uint8 ->
+ *   getRectSubPix(crop) -> resize(W,H)                      (utils/common.py:238-257)
+ * xyz [3,N] UNSHIFTED points (tensorInpaPoints), rgbd [4,N] (tensorInpaImage ++ tensorInpaDepth),
+ * poses_host: K poses in HOST memory (copied into kernel parameters, no H2D transfer),
+ * frames: device (or mapped pinned host) buffer [K,H,W,3] uint8, RGB order as the reference's numpyOutput. */
+int kb_render_frames(const float *xyz, const float *rgbd, long N, const kb_pose *poses_host, int K,
+                     const kb_frame_params *p, void *workspace, uint8_t *frames, kb_stream_t stream);
+
+/* ---- measurement hooks (bench.py) ---------------------------------------------------------------- */
+/* Stages of kb_render_frames, in launch order: 0 memset(accumulators) 1 init(z-buffer + resize tables)
+ * 2 splat_min 3 degrid 4 splat_accum 5 resolve+fill+quantise 6 crop+resize. */
+#define KB_FRAME_STAGES 7
+/* While enabled, kb_render_frames records CUDA events on its stream around every stage. */
+int kb_profile_enable(int on);
+/* Synchronises on the recorded events, returns the summed milliseconds per stage over all calls since the
+ * last read (stage_ms[KB_FRAME_STAGES]) and the number of calls; clears the record. */
+int kb_profile_read(double *stage_ms, long long *calls);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* KB200_H */

@@ -1,0 +1,411 @@
+// kb_render.cu -- render_pointcloud / fill_disocclusion of the reference as sm_100a kernels behind the C ABI.
+//
+// Reference: utils/common.py:428-686 (render_pointcloud: updateZee, updateDegrid, updateOutput, epilogue)
+//            utils/common.py:833-937 (fill_disocclusion), :104-109 (process_shift tensor half),
+//            :417-421 (median-5, here for binary masks).
+// These are the general (any B, any C, NCHW in/out) operators behind the reference's op API.  The fused
+// multi-pose frame loop lives in kb_frames.cu.
+//
+// All kernels are scatter / stencil / gather work bound by L2+HBM traffic and atomic throughput, not by
+// math: no tensor cores here.  Design notes (DESIGN.md has the numbers):
+//   * points are read coalesced from the reference's own SoA layout [B,3,N] / [B,C,N];
+//   * the z-buffer min is one native RED.MIN.S32 per point (positive floats order like ints);
+//   * accumulators are channels-last so that one point/neighbour issues ceil((C+1)/4) 16-byte
+//     RED.ADD.F32x4 instead of C+1 scalar atomics into planes H*W apart (20 -> 8 at C=4, 276 -> 72 at C=68);
+//   * grids are sized in whole waves of 148 SMs where the element count allows.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "kb_common.cuh"
+
+namespace kb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) k_fill_f32(float *__restrict__ p, long n, float v) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+__global__ void __launch_bounds__(256) k_shift_points(const float *__restrict__ xyz, const float *__restrict__ shift,
+                                                      float *__restrict__ out, long N) {
+  const int b = blockIdx.y;
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float *s = xyz + (long)b * 3 * N;
+  float x = s[n], y = s[N + n], z = s[2 * N + n];
+  shift_point(x, y, z, shift[b * 3 + 0], shift[b * 3 + 1], shift[b * 3 + 2]);
+  float *o = out + (long)b * 3 * N;
+  o[n] = x;
+  o[N + n] = y;
+  o[2 * N + n] = z;
+}
+
+struct Shift3 {
+  float x, y, z;
+  int on;
+};
+
+// updateZee: one thread per point.
+__global__ void __launch_bounds__(256) k_splat_min(const float *__restrict__ xyz, long N, Shift3 sh, Camera cam,
+                                                   float *__restrict__ zee, int32_t *__restrict__ pix_idx) {
+  const int b = blockIdx.y;
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float *s = xyz + (long)b * 3 * N;
+  float x = __ldg(s + n), y = __ldg(s + N + n), z = __ldg(s + 2 * N + n);
+  if (sh.on) shift_point(x, y, z, sh.x, sh.y, sh.z);
+  int32_t chosen = -1;
+  Proj p;
+  if (project(x, y, z, cam, p)) {
+    const int k = pick_neighbour(p);
+    if (k >= 0) {
+      const int px = p.nwx + (k & 1), py = p.nwy + (k >> 1);
+      if ((px >= 0) & (px < cam.W) & (py >= 0) & (py < cam.H)) {
+        chosen = py * cam.W + px;
+        zmin(zee + (long)b * cam.H * cam.W + chosen, p.err);
+      }
+    }
+  }
+  if (pix_idx) pix_idx[(long)b * N + n] = chosen;
+}
+
+// updateDegrid, race-free (read zin, write zout).  One thread per pixel; the 3x3 neighbourhood comes
+// through L1 (each value is reused by 9 threads of the same CTA row band).
+__global__ void __launch_bounds__(256) k_degrid(const float *__restrict__ zin, float *__restrict__ zout, int H, int W) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  const long base = (long)blockIdx.z * H * W;
+  const float *z = zin + base;
+  const float c = z[(long)y * W + x];
+  int count = 0;
+  float sum = 0.0f;
+  const int ox[4] = {1, 0, 1, 1};
+  const int oy[4] = {0, 1, 1, -1};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x1 = x + ox[k], y1 = y + oy[k], x2 = x - ox[k], y2 = y - oy[k];
+    if ((x1 < 0) | (x1 >= W) | (y1 < 0) | (y1 >= H)) continue;
+    if ((x2 < 0) | (x2 >= W) | (y2 < 0) | (y2 >= H)) continue;
+    const float a = z[(long)y1 * W + x1], d = z[(long)y2 * W + x2];
+    if ((double)c >= __dadd_rn((double)a, 1.0)) {
+      if ((double)c >= __dadd_rn((double)d, 1.0)) {
+        count += 2;
+        sum = __fadd_rn(sum, a);
+        sum = __fadd_rn(sum, d);
+      }
+    }
+  }
+  float r = c;
+  if (count > 0) r = fminf(c, __fdiv_rn(sum, (float)count));
+  zout[base + (long)y * W + x] = r;
+}
+
+// updateOutput: one thread per point; channels in groups of 4 -> one RED.ADD.F32x4 per neighbour and group.
+// data is the reference's [B,C,N]; the ones channel is synthesised (weight itself), :429.
+__global__ void __launch_bounds__(256) k_splat_accum(const float *__restrict__ xyz, const float *__restrict__ data,
+                                                     long N, int C, int Cp, Shift3 sh, Camera cam,
+                                                     const float *__restrict__ zee, float *__restrict__ accum) {
+  const int b = blockIdx.y;
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float *s = xyz + (long)b * 3 * N;
+  float x = __ldg(s + n), y = __ldg(s + N + n), z = __ldg(s + 2 * N + n);
+  if (sh.on) shift_point(x, y, z, sh.x, sh.y, sh.z);
+  Proj p;
+  if (!project(x, y, z, cam, p)) return;
+  const long P = (long)cam.H * cam.W;
+  const float *zb = zee + (long)b * P;
+  float w[4] = {p.wnw, p.wne, p.wsw, p.wse};
+  long pix[4];
+  bool on[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int px = p.nwx + (k & 1), py = p.nwy + (k >> 1);
+    on[k] = (px >= 0) & (px < cam.W) & (py >= 0) & (py < cam.H);
+    pix[k] = on[k] ? (long)py * cam.W + px : 0;
+    if (on[k]) on[k] = z_gate(p.err, __ldg(zb + pix[k]));
+    // a zero weight adds exact zeros to every channel: skipping it changes no sum
+    if (on[k]) on[k] = (w[k] != 0.0f);
+  }
+  if (!(on[0] | on[1] | on[2] | on[3])) return;
+  const float *d = data + (long)b * C * N + n;
+  float *ab = accum + (long)b * P * Cp;
+  for (int c0 = 0; c0 < Cp; c0 += 4) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + j;
+      v[j] = (c < C) ? __ldg(d + (long)c * N) : (c == C ? 1.0f : 0.0f);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!on[k]) continue;
+      red_add_v4(ab + pix[k] * Cp + c0, __fmul_rn(v[0], w[k]), __fmul_rn(v[1], w[k]), __fmul_rn(v[2], w[k]),
+                 __fmul_rn(v[3], w[k]));
+    }
+  }
+}
+
+// epilogue :686 -- channels-last accumulators -> NCHW render + existing.  A CTA handles 32 pixels x all
+// channels through shared memory so that both the channels-last reads and the planar writes coalesce.
+__global__ void __launch_bounds__(256) k_normalize(const float *__restrict__ accum, int C, int Cp, long P,
+                                                   float *__restrict__ render, float *__restrict__ existing) {
+  extern __shared__ float tile[];  // [32][Cp+1]
+  const int b = blockIdx.y;
+  const long p0 = (long)blockIdx.x * 32;
+  const int npx = (int)min((long)32, P - p0);
+  const float *src = accum + ((long)b * P + p0) * Cp;
+  const int ld = Cp + 1;
+  for (int i = threadIdx.x; i < npx * Cp; i += blockDim.x) tile[(i / Cp) * ld + (i % Cp)] = src[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane < npx) {
+    const float wsum = tile[lane * ld + C];
+    const float den = __fadd_rn(wsum, 0.0000001f);
+    for (int c = wrp; c < C; c += nw) render[((long)b * C + c) * P + p0 + lane] = __fdiv_rn(tile[lane * ld + c], den);
+    if (wrp == 0) existing[(long)b * P + p0 + lane] = wsum;
+  }
+}
+
+// fill_disocclusion :837-924, one thread per pixel (only hole pixels do any work).
+__global__ void __launch_bounds__(256) k_fill(const float *__restrict__ input, const float *__restrict__ depth,
+                                              float *__restrict__ output, int C, int H, int W) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  const int b = blockIdx.z;
+  const long P = (long)H * W;
+  const float *dep = depth + (long)b * P;
+  const float *in = input + (long)b * C * P;
+  float *out = output + (long)b * C * P;
+  const long me = (long)y * W + x;
+  int fx = x, fy = y;
+  if (!(dep[me] > 0.0f)) {
+    float shortest = 1000000.0f;
+    fx = -1;
+    fy = -1;
+    for (int k = 0; k < 16; ++k) {
+      const float dx = c_dirx[k], dy = c_diry[k];
+      float ax = (float)x, ay = (float)y, bx = (float)x, by = (float)y;
+      int iax, iay, ibx, iby;
+      for (;;) {
+        ax = __fsub_rn(ax, dx); iax = (int)roundf(ax);
+        ay = __fsub_rn(ay, dy); iay = (int)roundf(ay);
+        if ((iax < 0) | (iax >= W)) break;
+        if ((iay < 0) | (iay >= H)) break;
+        if (dep[(long)iay * W + iax] > 0.0f) break;
+      }
+      if ((iax < 0) | (iax >= W)) continue;
+      if ((iay < 0) | (iay >= H)) continue;
+      for (;;) {
+        bx = __fadd_rn(bx, dx); ibx = (int)roundf(bx);
+        by = __fadd_rn(by, dy); iby = (int)roundf(by);
+        if ((ibx < 0) | (ibx >= W)) break;
+        if ((iby < 0) | (iby >= H)) break;
+        if (dep[(long)iby * W + ibx] > 0.0f) break;
+      }
+      if ((ibx < 0) | (ibx >= W)) continue;
+      if ((iby < 0) | (iby >= H)) continue;
+      const float ddx = (float)(ibx - iax), ddy = (float)(iby - iay);
+      const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)));
+      if (shortest > dist) {
+        fx = iax; fy = iay;
+        if (dep[(long)iay * W + iax] < dep[(long)iby * W + ibx]) { fx = ibx; fy = iby; }
+        shortest = dist;
+      }
+    }
+    if (fx == -1 || fy == -1) { fx = x; fy = y; }   // no ray found: keep the clone's value
+  }
+  const long from = (long)fy * W + fx;
+  for (int c = 0; c < C; ++c) out[(long)c * P + me] = in[(long)c * P + from];
+}
+
+// median-5 on a {0,1} map with reflect padding == (5x5 count >= 13), :417-421.
+__global__ void __launch_bounds__(256) k_median5_binary(const float *__restrict__ in, float *__restrict__ out, int H, int W) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  const long base = (long)blockIdx.z * H * W;
+  int cnt = 0;
+#pragma unroll
+  for (int dy = -2; dy <= 2; ++dy) {
+    int yy = y + dy;
+    yy = yy < 0 ? -yy : (yy >= H ? 2 * H - 2 - yy : yy);
+#pragma unroll
+    for (int dx = -2; dx <= 2; ++dx) {
+      int xx = x + dx;
+      xx = xx < 0 ? -xx : (xx >= W ? 2 * W - 2 - xx : xx);
+      cnt += in[base + (long)yy * W + xx] > 0.5f;
+    }
+  }
+  out[base + (long)y * W + x] = cnt >= 13 ? 1.0f : 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host helpers
+// ---------------------------------------------------------------------------------------------------
+
+Camera make_camera(double focal, double baseline, int H, int W) {
+  Camera c;
+  c.f32 = (float)focal;
+  c.fB = focal * baseline;
+  c.halfW = 0.5 * (double)W;
+  c.halfH = 0.5 * (double)H;
+  c.W = W;
+  c.H = H;
+  return c;
+}
+
+static Shift3 make_shift(const float *shift_host) {
+  Shift3 s{0.f, 0.f, 0.f, 0};
+  if (shift_host) {
+    s.x = shift_host[0];
+    s.y = shift_host[1];
+    s.z = shift_host[2];
+    s.on = 1;
+  }
+  return s;
+}
+
+}  // namespace kb
+
+using namespace kb;
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+int kb_version(void) { return 100; }
+const char *kb_last_error(void) { return g_err; }
+long long kb_launch_count(void) { return g_launches.load(); }
+
+int kb_shift_points(const float *xyz, const float *shift, float *out, int B, long N, kb_stream_t stream) {
+  KB_REQUIRE(xyz && shift && out && B > 0 && N > 0, "kb_shift_points: bad arguments");
+  dim3 grid(cdiv(N, 256), B);
+  k_shift_points<<<grid, 256, 0, (cudaStream_t)stream>>>(xyz, shift, out, N);
+  count_launch();
+  return check_launch("kb_shift_points");
+}
+
+int kb_splat_min(const float *xyz, int B, long N, const float *shift_host, double focal, double baseline,
+                 float *zee, int H, int W, int32_t *pix_idx, kb_stream_t stream) {
+  KB_REQUIRE(xyz && zee && B > 0 && N > 0 && H > 0 && W > 0, "kb_splat_min: bad arguments");
+  KB_REQUIRE((long)H * W < (1L << 31), "kb_splat_min: image too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long nz = (long)B * H * W;
+  k_fill_f32<<<min(cdiv(nz, 256), 148u * 8u), 256, 0, st>>>(zee, nz, 1000000.0f);
+  dim3 grid(cdiv(N, 256), B);
+  k_splat_min<<<grid, 256, 0, st>>>(xyz, N, make_shift(shift_host), make_camera(focal, baseline, H, W), zee, pix_idx);
+  count_launch(2);
+  return check_launch("kb_splat_min");
+}
+
+int kb_degrid(const float *zee_in, float *zee_out, int B, int H, int W, kb_stream_t stream) {
+  KB_REQUIRE(zee_in && zee_out && zee_in != zee_out && B > 0 && H > 0 && W > 0, "kb_degrid: bad arguments");
+  dim3 grid(cdiv(W, 32), cdiv(H, 8), B);
+  k_degrid<<<grid, 256, 0, (cudaStream_t)stream>>>(zee_in, zee_out, H, W);
+  count_launch();
+  return check_launch("kb_degrid");
+}
+
+int kb_accum_channels(int C) { return (C + 1 + 3) & ~3; }
+
+int kb_splat_accum(const float *xyz, const float *data, int B, long N, int C, const float *shift_host,
+                   double focal, double baseline, const float *zee, float *accum, int H, int W,
+                   kb_stream_t stream) {
+  KB_REQUIRE(xyz && data && zee && accum && B > 0 && N > 0 && C > 0 && H > 0 && W > 0, "kb_splat_accum: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Cp = kb_accum_channels(C);
+  cudaError_t e = cudaMemsetAsync(accum, 0, sizeof(float) * (size_t)B * H * W * Cp, st);
+  if (e != cudaSuccess) {
+    set_error("kb_splat_accum memset: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  dim3 grid(cdiv(N, 256), B);
+  k_splat_accum<<<grid, 256, 0, st>>>(xyz, data, N, C, Cp, make_shift(shift_host), make_camera(focal, baseline, H, W),
+                                      zee, accum);
+  count_launch(2);
+  return check_launch("kb_splat_accum");
+}
+
+int kb_normalize(const float *accum, int B, int C, int H, int W, float *render, float *existing,
+                 kb_stream_t stream) {
+  KB_REQUIRE(accum && render && existing && B > 0 && C > 0 && H > 0 && W > 0, "kb_normalize: bad arguments");
+  const int Cp = kb_accum_channels(C);
+  const long P = (long)H * W;
+  dim3 grid(cdiv(P, 32), B);
+  const size_t smem = sizeof(float) * 32 * (Cp + 1);
+  k_normalize<<<grid, 256, smem, (cudaStream_t)stream>>>(accum, C, Cp, P, render, existing);
+  count_launch();
+  return check_launch("kb_normalize");
+}
+
+size_t kb_render_workspace_bytes(int B, int C, int H, int W) {
+  const size_t P = (size_t)H * W;
+  return sizeof(float) * (size_t)B * P * (2 + (size_t)kb_accum_channels(C));
+}
+
+int kb_render_pointcloud(const float *xyz, const float *data, int B, long N, int C, int W, int H,
+                         double focal, double baseline, float *render, float *existing, void *workspace,
+                         kb_stream_t stream) {
+  KB_REQUIRE(workspace, "kb_render_pointcloud: workspace is null");
+  const size_t P = (size_t)H * W;
+  float *z0 = (float *)workspace;
+  float *z1 = z0 + (size_t)B * P;
+  float *acc = z1 + (size_t)B * P;
+  int rc = kb_splat_min(xyz, B, N, nullptr, focal, baseline, z0, H, W, nullptr, stream);
+  if (rc) return rc;
+  rc = kb_degrid(z0, z1, B, H, W, stream);
+  if (rc) return rc;
+  rc = kb_splat_accum(xyz, data, B, N, C, nullptr, focal, baseline, z1, acc, H, W, stream);
+  if (rc) return rc;
+  return kb_normalize(acc, B, C, H, W, render, existing, stream);
+}
+
+int kb_fill(const float *input, const float *depth, float *output, int B, int C, int H, int W,
+            kb_stream_t stream) {
+  KB_REQUIRE(input && depth && output && input != output && B > 0 && C > 0 && H > 0 && W > 0, "kb_fill: bad arguments");
+  dim3 grid(cdiv(W, 32), cdiv(H, 8), B);
+  k_fill<<<grid, 256, 0, (cudaStream_t)stream>>>(input, depth, output, C, H, W);
+  count_launch();
+  return check_launch("kb_fill");
+}
+
+int kb_median5_binary(const float *in, float *out, int B, int H, int W, kb_stream_t stream) {
+  KB_REQUIRE(in && out && in != out && B > 0 && H > 2 && W > 2, "kb_median5_binary: bad arguments");
+  dim3 grid(cdiv(W, 32), cdiv(H, 8), B);
+  k_median5_binary<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, H, W);
+  count_launch();
+  return check_launch("kb_median5_binary");
+}
+
+}  // extern "C"

@@ -1,0 +1,296 @@
+"""Host-side mirror of the reference's view-synthesis operators (utils/common.py in pierlj/ken-burns-effect).
+
+Same function names, argument meaning and return values as the reference so that `models/*` and
+`utils/pipeline.py` style callers work unchanged, but every CUDA kernel the reference JIT-compiles from a
+source string (utils/common.py:428-937) is replaced by a call into libkb200.so (include/kb200.h), and the
+per-frame loop of process_kenburns (utils/common.py:222-260) is one fused multi-pose call.
+
+There is no CPU path for the kernels: tensors must live on a CUDA device and the shared library must be
+present, otherwise a RuntimeError is raised.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from .. import _native as nat
+
+# frames rendered per fused launch group (kb_render_frames); bounded by KB_MAX_POSES
+FRAME_BATCH = 16
+
+
+def _stream():
+    # queried per call: the reference captures the stream once at import (utils/common.py:267-269)
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("ken_burns_effect_b200 kernels need CUDA tensors (there is no CPU fallback)")
+        if t.dtype != torch.float32:
+            raise RuntimeError("ken_burns_effect_b200 kernels are fp32-in/fp32-out like the reference")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# geometry helpers (reference: utils/common.py:382-426)
+# ---------------------------------------------------------------------------------------------------------
+
+def depth_to_points(tensorDepth, dblFocal):
+    """Pinhole back-projection, utils/common.py:382-392.  [B,1,H,W] -> [B,3,H,W].
+
+    The pixel-centre ramps are built exactly like the reference (CPU torch.linspace, then * (1/f) in fp32,
+    then moved to the depth's device) so that the products are bit-identical.
+    """
+    B, _, H, W = tensorDepth.shape
+    inv_f = 1.0 / dblFocal
+    u = (torch.linspace(-0.5 * W + 0.5, 0.5 * W - 0.5, W) * inv_f).view(1, 1, 1, W).to(tensorDepth)
+    v = (torch.linspace(-0.5 * H + 0.5, 0.5 * H - 0.5, H) * inv_f).view(1, 1, H, 1).to(tensorDepth)
+    return torch.cat([tensorDepth * u, tensorDepth * v, tensorDepth], 1)
+
+
+_LAPLACE_TAPS = ((0, 1, -1.0), (0, 2, -1.0), (1, 1, 4.0), (1, 0, -1.0), (2, 0, -1.0))
+
+
+def spatial_filter(tensorInput, strType):
+    """utils/common.py:394-426: 'laplacian' (the reference's asymmetric 5-tap kernel, replicate padding),
+    'median-3' / 'median-5' (reflect padding)."""
+    if strType == 'laplacian':
+        C = tensorInput.size(1)
+        k = tensorInput.new_zeros(C, C, 3, 3)
+        for c in range(C):
+            for (r, s, val) in _LAPLACE_TAPS:
+                k[c, c, r, s] = val
+        padded = torch.nn.functional.pad(tensorInput, [1, 1, 1, 1], mode='replicate')
+        return torch.nn.functional.conv2d(padded, k)
+
+    if strType in ('median-3', 'median-5'):
+        r = 1 if strType == 'median-3' else 2
+        if strType == 'median-5' and tensorInput.is_cuda and tensorInput.size(1) == 1 \
+                and bool(((tensorInput == 0) | (tensorInput == 1)).all()):
+            # binary map: the 25-way median is (5x5 box count >= 13); one kernel instead of a
+            # [B,1,H,W,25] unfold (79 MB at 1024x768) + sort
+            return median5_binary(tensorInput)
+        n = 2 * r + 1
+        x = torch.nn.functional.pad(tensorInput, [r, r, r, r], mode='reflect')
+        x = x.unfold(2, n, 1).unfold(3, n, 1).contiguous()
+        x = x.view(x.size(0), x.size(1), x.size(2), x.size(3), n * n)
+        return x.median(-1, False)[0]
+    return None
+
+
+def median5_binary(tensorMask):
+    """spatial_filter(mask, 'median-5') for a {0,1} mask [B,1,H,W] (utils/common.py:417-421)."""
+    _need_cuda(tensorMask)
+    x = tensorMask.contiguous()
+    out = torch.empty_like(x)
+    B, _, H, W = x.shape
+    nat.check(nat.lib().kb_median5_binary(_ptr(x), _ptr(out), B, H, W, _stream()), "kb_median5_binary")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# render_pointcloud / fill_disocclusion (reference: utils/common.py:428-686, :833-937)
+# ---------------------------------------------------------------------------------------------------------
+
+def render_pointcloud(tensorInput, tensorData, intWidth, intHeight, dblFocal, dblBaseline, return_zee=False):
+    """Z-buffered bilinear splat.  tensorInput [B,3,N] (already shifted points), tensorData [B,C,N] ->
+    (tensorRender [B,C,H,W], tensorExisting [B,1,H,W]); same contract as utils/common.py:428."""
+    _need_cuda(tensorInput, tensorData)
+    pts = tensorInput.contiguous()
+    dat = tensorData.contiguous()
+    B, C, N = dat.shape
+    if pts.shape != (B, 3, N):
+        raise RuntimeError(f"render_pointcloud: points {tuple(pts.shape)} do not match data {tuple(dat.shape)}")
+    H, W = int(intHeight), int(intWidth)
+    L = nat.lib()
+    render = torch.empty(B, C, H, W, device=pts.device, dtype=torch.float32)
+    existing = torch.empty(B, 1, H, W, device=pts.device, dtype=torch.float32)
+    ws = torch.empty(L.kb_render_workspace_bytes(B, C, H, W), device=pts.device, dtype=torch.uint8)
+    nat.check(L.kb_render_pointcloud(_ptr(pts), _ptr(dat), B, N, C, W, H, float(dblFocal), float(dblBaseline),
+                                     _ptr(render), _ptr(existing), _ptr(ws), _stream()), "kb_render_pointcloud")
+    if return_zee:
+        P = H * W
+        z = ws[:8 * B * P].view(torch.float32)
+        return render, existing, z[:B * P].view(B, 1, H, W).clone(), z[B * P:].view(B, 1, H, W).clone()
+    return render, existing
+
+
+def fill_disocclusion(tensorInput, tensorDepth):
+    """utils/common.py:833-937.  [B,C,H,W], [B,1,H,W] -> filled copy of the input."""
+    _need_cuda(tensorInput, tensorDepth)
+    x = tensorInput.contiguous()
+    d = tensorDepth.contiguous()
+    B, C, H, W = x.shape
+    out = torch.empty_like(x)
+    nat.check(nat.lib().kb_fill(_ptr(x), _ptr(d), _ptr(out), B, C, H, W, _stream()), "kb_fill")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# camera path (reference: utils/common.py:83-112, :172-263)
+# ---------------------------------------------------------------------------------------------------------
+
+def _shift_scalars(objectSettings, objectCommon, dblFocal):
+    """Python-double camera shift of process_shift, utils/common.py:88-100 (incl. the crop-relative argmin
+    location quirk: objectDepthrange[2] is relative to the [128:-128] crop and stays so)."""
+    rng = objectCommon['objectDepthrange']
+    closest = rng[0] + (objectSettings['dblDepthTo'] - objectSettings['dblDepthFrom'])
+    from_u, from_v = rng[2][0], rng[2][1]
+    to_u = from_u + objectSettings['dblShiftU']
+    to_v = from_v + objectSettings['dblShiftV']
+    half_w = objectCommon['intWidth'] / 2.0
+    half_h = objectCommon['intHeight'] / 2.0
+    from_x = ((from_u - half_w) * closest) / dblFocal
+    from_y = ((from_v - half_h) * closest) / dblFocal
+    to_x = ((to_u - half_w) * closest) / dblFocal
+    to_y = ((to_v - half_h) * closest) / dblFocal
+    return from_x - to_x, from_y - to_y, objectSettings['dblDepthTo'] - objectSettings['dblDepthFrom']
+
+
+def process_shift(objectSettings, objectCommon, dblFocal=None):
+    """utils/common.py:83-112 -> (shifted points [B,3,N], tensorShift [1,3,1])."""
+    if dblFocal is None:
+        dblFocal = objectCommon['dblFocal']
+    sx, sy, sz = _shift_scalars(objectSettings, objectCommon, dblFocal)
+    pts = objectSettings['tensorPoints']
+    _need_cuda(pts)
+    tensorShift = torch.FloatTensor([sx, sy, sz]).view(1, 3, 1).to(pts.device)
+    src = pts.contiguous()
+    B, _, N = src.shape
+    out = torch.empty_like(src)
+    sh = tensorShift.view(1, 3).expand(B, 3).contiguous()
+    nat.check(nat.lib().kb_shift_points(_ptr(src), _ptr(sh), _ptr(out), B, N, _stream()), "kb_shift_points")
+    return out, tensorShift
+
+
+def _pose_settings(objectSettings, objectCommon, dblStep):
+    """Per-step camera scalars of process_kenburns, utils/common.py:182-198 and :223-236."""
+    dblFrom = 1.0 - dblStep
+    dblTo = 1.0 - dblFrom
+    f_w = objectSettings['objectFrom']['intCropWidth']
+    t_w = objectSettings['objectTo']['intCropWidth']
+    if objectSettings['dolly']:
+        focalScaling = t_w / f_w
+        currentFocal = objectCommon['dblFocal'] * (1 - dblStep) + dblStep * objectCommon['dblFocal'] * focalScaling
+    else:
+        currentFocal = objectCommon['dblFocal']
+    dblShiftU = ((dblFrom * objectSettings['objectFrom']['dblCenterU']) + (dblTo * objectSettings['objectTo']['dblCenterU'])) - (objectCommon['intWidth'] / 2.0)
+    dblShiftV = ((dblFrom * objectSettings['objectFrom']['dblCenterV']) + (dblTo * objectSettings['objectTo']['dblCenterV'])) - (objectCommon['intHeight'] / 2.0)
+    dblCropWidth = (dblFrom * f_w) + (dblTo * t_w)
+    dblDepthFrom = objectCommon['objectDepthrange'][0]
+    dblDepthTo = objectCommon['objectDepthrange'][0] * (dblCropWidth / max(f_w, t_w))
+    return {'dblShiftU': dblShiftU, 'dblShiftV': dblShiftV, 'dblDepthFrom': dblDepthFrom,
+            'dblDepthTo': dblDepthTo}, currentFocal
+
+
+def kenburns_poses(objectSettings, objectCommon):
+    """[(shift_xyz as fp32 triple, focal double)] for every step of objectSettings['dblSteps']."""
+    poses = []
+    for dblStep in objectSettings['dblSteps']:
+        st, focal = _pose_settings(objectSettings, objectCommon, dblStep)
+        sx, sy, sz = _shift_scalars(st, objectCommon, focal)
+        sh = np.array([sx, sy, sz], dtype=np.float64).astype(np.float32)   # torch.FloatTensor([...]) rounding
+        poses.append((sh, float(focal)))
+    return poses
+
+
+def process_inpaint(tensorShift, objectCommon, moduleInpaint, dblFocal):
+    """utils/common.py:47-81 (single-network branch; the list branch of the reference references an
+    undefined name and cannot run)."""
+    if isinstance(moduleInpaint, list):
+        moduleInpaint = moduleInpaint[0]
+    obj = moduleInpaint.pointcloud_inpainting(objectCommon['tensorRawImage'], objectCommon['tensorRawDisparity'],
+                                              tensorShift, objectCommon, dblFocal)
+    disp = obj['tensorDisparity']
+    depth = (dblFocal * objectCommon['dblBaseline']) / (disp + 0.0000001)
+    valid = (spatial_filter(disp / disp.max(), 'laplacian').abs() < 0.03).float()
+    points = depth_to_points(depth * valid, dblFocal).view(1, 3, -1) - tensorShift
+    # points that were missing in the shifted view get appended to the cloud (:75-80).  The reference tests
+    # 'tensorExisting' of the network output; modules may expose the input mask separately (PartialInpaint).
+    existing = obj.get('tensorExistingInput', obj['tensorExisting'])
+    mask = (existing[:, 0:1] == 0.0).view(-1)
+    idx = mask.nonzero(as_tuple=True)[0]
+    objectCommon['tensorInpaImage'] = torch.cat([objectCommon['tensorInpaImage'], obj['tensorImage'].view(1, 3, -1)[:, :, idx]], 2)
+    objectCommon['tensorInpaDisparity'] = torch.cat([objectCommon['tensorInpaDisparity'], disp.view(1, 1, -1)[:, :, idx]], 2)
+    objectCommon['tensorInpaDepth'] = torch.cat([objectCommon['tensorInpaDepth'], depth.view(1, 1, -1)[:, :, idx]], 2)
+    objectCommon['tensorInpaPoints'] = torch.cat([objectCommon['tensorInpaPoints'], points[:, :, idx]], 2)
+
+
+class FrameRenderer:
+    """Fused per-frame loop (utils/common.py:238-257) over one point cloud: K poses per call of
+    kb_render_frames, frames land in pinned host memory through an async copy."""
+
+    def __init__(self, tensorPoints, tensorImage, tensorDepth, intWidth, intHeight, dblBaseline, crop_w, crop_h,
+                 batch=FRAME_BATCH):
+        _need_cuda(tensorPoints, tensorImage, tensorDepth)
+        self.device = tensorPoints.device
+        self.N = tensorPoints.shape[-1]
+        self.xyz = tensorPoints.reshape(3, self.N).contiguous()
+        self.rgbd = torch.cat([tensorImage.reshape(3, self.N), tensorDepth.reshape(1, self.N)], 0).contiguous()
+        self.H, self.W = int(intHeight), int(intWidth)
+        self.batch = max(1, min(int(batch), nat.KB_MAX_POSES))
+        self.params = nat.KBFrameParams(self.H, self.W, int(crop_w), int(crop_h), float(dblBaseline))
+        L = nat.lib()
+        nbytes = L.kb_frames_workspace_bytes(ctypes.byref(self.params), self.batch)
+        self.ws = torch.empty(nbytes + 256, device=self.device, dtype=torch.uint8)
+        off = (-self.ws.data_ptr()) % 256
+        self.ws_ptr = self.ws.data_ptr() + off
+        self.dev_frames = torch.empty(self.batch, self.H, self.W, 3, device=self.device, dtype=torch.uint8)
+
+    def render_into(self, poses, out_frames):
+        """poses: list of (shift fp32[3], focal); out_frames: uint8 tensor [len(poses),H,W,3] (device or
+        pinned host).  Enqueue only -- the caller synchronises."""
+        L = nat.lib()
+        n = len(poses)
+        done = 0
+        while done < n:
+            k = min(self.batch, n - done)
+            arr = (nat.KBPose * k)()
+            for i in range(k):
+                sh, focal = poses[done + i]
+                arr[i].shift[0], arr[i].shift[1], arr[i].shift[2] = float(sh[0]), float(sh[1]), float(sh[2])
+                arr[i].focal = float(focal)
+            dst = out_frames[done:done + k]
+            target = dst if dst.is_cuda else self.dev_frames[:k]
+            nat.check(L.kb_render_frames(_ptr(self.xyz), _ptr(self.rgbd), self.N, arr, k, ctypes.byref(self.params),
+                                         ctypes.c_void_p(self.ws_ptr), _ptr(target), _stream()), "kb_render_frames")
+            if not dst.is_cuda:
+                dst.copy_(target, non_blocking=True)
+            done += k
+        return out_frames
+
+
+def process_kenburns(objectSettings, objectCommon, moduleInpaint):
+    """utils/common.py:172-263 -> list of uint8 [H,W,3] frames (RGB order of the input tensor's channels)."""
+    dev = objectCommon['tensorRawPoints'].device
+    if 'boolInpaint' not in objectSettings or objectSettings['boolInpaint'] == True:  # noqa: E712
+        objectCommon['tensorInpaImage'] = objectCommon['tensorRawImage'].view(1, 3, -1)
+        objectCommon['tensorInpaDisparity'] = objectCommon['tensorRawDisparity'].view(1, 1, -1)
+        objectCommon['tensorInpaDepth'] = objectCommon['tensorRawDepth'].view(1, 1, -1)
+        objectCommon['tensorInpaPoints'] = objectCommon['tensorRawPoints'].view(1, 3, -1)
+        for dblStep in [0.0, 1.0]:
+            st, focal = _pose_settings(objectSettings, objectCommon, dblStep)
+            sx, sy, sz = _shift_scalars(st, objectCommon, focal)
+            tensorShift = torch.FloatTensor([sx, sy, sz]).view(1, 3, 1).to(dev)
+            # (the reference also renders the current cloud here, :208-215, and discards the result)
+            if not objectSettings['dolly']:
+                process_inpaint(1.1 * tensorShift, objectCommon, moduleInpaint, focal)
+
+    f, t = objectSettings['objectFrom'], objectSettings['objectTo']
+    crop_w = max(f['intCropWidth'], t['intCropWidth'])
+    crop_h = max(f['intCropHeight'], t['intCropHeight'])
+    poses = kenburns_poses(objectSettings, objectCommon)
+    renderer = FrameRenderer(objectCommon['tensorInpaPoints'], objectCommon['tensorInpaImage'],
+                             objectCommon['tensorInpaDepth'], objectCommon['intWidth'], objectCommon['intHeight'],
+                             objectCommon['dblBaseline'], crop_w, crop_h)
+    host = torch.empty(len(poses), renderer.H, renderer.W, 3, dtype=torch.uint8).pin_memory()
+    renderer.render_into(poses, host)
+    torch.cuda.current_stream().synchronize()
+    frames = host.numpy()
+    return [frames[i] for i in range(len(poses))]

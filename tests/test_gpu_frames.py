@@ -1,0 +1,101 @@
+"""GPU parity of the fused per-frame loop (kb_render_frames) against the CPU oracle's restatement of
+utils/common.py:238-257 (process_shift -> render -> fill -> uint8 -> getRectSubPix -> resize).
+
+uint8 frames: the fp32 accumulation order differs between any two runs of the reference itself (float
+atomicAdd), so a value sitting within 1 ulp of an integer boundary may truncate differently: the bar is
+max |diff| <= 1 on a vanishing fraction of bytes, everything else exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from ken_burns_effect_b200.utils import common as kb
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _render_frames(pts, rgb, dep, common, W, H, steps, dolly=False, batch=16):
+    st = helpers.settings(common, W, H, steps, dolly)
+    poses = kb.kenburns_poses(st, common)
+    f, t = st['objectFrom'], st['objectTo']
+    cw, ch = max(f['intCropWidth'], t['intCropWidth']), max(f['intCropHeight'], t['intCropHeight'])
+    r = kb.FrameRenderer(torch.from_numpy(pts).cuda(), torch.from_numpy(rgb).cuda(), torch.from_numpy(dep).cuda(),
+                         W, H, common['dblBaseline'], cw, ch, batch=batch)
+    out = torch.empty(len(poses), H, W, 3, dtype=torch.uint8, device="cuda")
+    r.render_into(poses, out)
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), poses, (cw, ch)
+
+
+def _oracle_frames(pts, rgb, dep, common, W, H, poses, crop):
+    data = np.concatenate([rgb, dep], 0)
+    frames = []
+    for sh, focal in poses:
+        shifted = oracle.shift_points(pts, sh)
+        frames.append(oracle.frame(shifted, data, W, H, focal, common['dblBaseline'], crop[0], crop[1]))
+    return np.stack(frames)
+
+
+def _compare(mine, ref):
+    d = np.abs(mine.astype(np.int16) - ref.astype(np.int16))
+    frac = float((d > 0).mean())
+    assert d.max() <= 1, f"max byte diff {d.max()}"
+    assert frac < 1e-4, f"{frac:.2e} of bytes differ"
+    assert helpers.rel_l2(mine, ref) < 1e-3
+
+
+@pytest.mark.parametrize("W,H,focal,extra,dolly", [
+    (64, 48, 32.0, 0, False),
+    (256, 192, 128.0, 4099, False),
+    (256, 192, 128.0, 0, True),
+    (250, 190, 125.0, 33, False),       # W not a multiple of 4, even crop sizes -> sub-pixel getRectSubPix
+])
+def test_frames_small(W, H, focal, extra, dolly):
+    oracle.set_threads(0)
+    pts, rgb, dep, common = helpers.scene(W, H, focal, extra)
+    steps = np.linspace(0.0, 1.0, 5).tolist()
+    mine, poses, crop = _render_frames(pts, rgb, dep, common, W, H, steps, dolly, batch=3)
+    ref = _oracle_frames(pts, rgb, dep, common, W, H, poses, crop)
+    _compare(mine, ref)
+
+
+def test_frames_full_size_two_poses():
+    oracle.set_threads(0)
+    W, H, focal = 1024, 768, 512.0
+    pts, rgb, dep, common = helpers.scene(W, H, focal, 70001)
+    mine, poses, crop = _render_frames(pts, rgb, dep, common, W, H, [0.0, 1.0])
+    ref = _oracle_frames(pts, rgb, dep, common, W, H, poses, crop)
+    _compare(mine, ref)
+
+
+def test_frames_batching_invariance():
+    """Size-independent property at full size: the frames do not depend on how poses are batched, and the
+    z-buffer/hole structure is deterministic -> at most summation-order noise between batchings."""
+    W, H, focal = 1024, 768, 512.0
+    pts, rgb, dep, common = helpers.scene(W, H, focal, 0)
+    steps = np.linspace(0.0, 1.0, 7).tolist()
+    a, _, _ = _render_frames(pts, rgb, dep, common, W, H, steps, batch=7)
+    b, _, _ = _render_frames(pts, rgb, dep, common, W, H, steps, batch=2)
+    d = np.abs(a.astype(np.int16) - b.astype(np.int16))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-4
+
+
+def test_process_kenburns_matches_frame_loop():
+    """The public process_kenburns (host frames in pinned memory) equals the device-side loop."""
+    W, H, focal = 256, 192, 128.0
+    pts, rgb, dep, common = helpers.scene(W, H, focal, 0)
+    steps = np.linspace(0.0, 1.0, 4).tolist()
+    st = helpers.settings(common, W, H, steps, dolly=True)   # dolly: no inpainting stage
+    common = dict(common)
+    P = W * H
+    common['tensorRawImage'] = torch.from_numpy(rgb).cuda().view(1, 3, H, W)
+    common['tensorRawDepth'] = torch.from_numpy(dep).cuda().view(1, 1, H, W)
+    common['tensorRawDisparity'] = (focal * 120) / (common['tensorRawDepth'] + 1e-7)
+    common['tensorRawPoints'] = torch.from_numpy(pts).cuda().view(1, 3, P)
+    frames = kb.process_kenburns(st, common, None)
+    mine, _, _ = _render_frames(pts, rgb, dep, common, W, H, steps, dolly=True)
+    assert len(frames) == 4 and frames[0].shape == (H, W, 3) and frames[0].dtype == np.uint8
+    d = np.abs(np.stack(frames).astype(np.int16) - mine.astype(np.int16))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-4
