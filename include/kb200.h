@@ -119,8 +119,8 @@ int kb_render_frames(const float *xyz, const float *rgbd, long N, const kb_pose 
 
 /* ---- measurement hooks (bench.py) ---------------------------------------------------------------- */
 /* Stages of kb_render_frames, in launch order: 0 memset(accumulators) 1 init(z-buffer + resize tables)
- * 2 splat_min 3 degrid 4 splat_accum 5 resolve+fill+quantise 6 crop+resize. */
-#define KB_FRAME_STAGES 7
+ * 2 splat_min 3 degrid 4 splat_accum 5 resolve (normalise+quantise+hole list) 6 fill 7 crop+resize. */
+#define KB_FRAME_STAGES 8
 /* While enabled, kb_render_frames records CUDA events on its stream around every stage. */
 int kb_profile_enable(int on);
 /* Synchronises on the recorded events, returns the summed milliseconds per stage over all calls since the

@@ -51,7 +51,7 @@ SIGNATURES = {
     "kb_profile_read": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]),
 }
 
-FRAME_STAGES = ("memset_accum", "init_zbuf_tables", "splat_min", "degrid", "splat_accum", "resolve_fill", "crop_resize")
+FRAME_STAGES = ("memset_accum", "init_zbuf_tables", "splat_min", "degrid", "splat_accum", "resolve", "fill", "crop_resize")
 
 _lib = None
 

@@ -121,6 +121,25 @@ def render_pointcloud(tensorInput, tensorData, intWidth, intHeight, dblFocal, db
     return render, existing
 
 
+def accumulate_with_zee(tensorInput, tensorData, tensorZee, dblFocal, dblBaseline):
+    """Passes 3+4 of render_pointcloud (updateOutput + epilogue, utils/common.py:585-686) against a z-buffer
+    supplied by the caller ([B,1,H,W], already degridded).  Lets a test isolate the accumulation from the
+    reference's racy degrid pass."""
+    _need_cuda(tensorInput, tensorData, tensorZee)
+    pts, dat, zee = tensorInput.contiguous(), tensorData.contiguous(), tensorZee.contiguous()
+    B, C, N = dat.shape
+    H, W = zee.shape[-2:]
+    L = nat.lib()
+    Cp = L.kb_accum_channels(C)
+    acc = torch.empty(B, H, W, Cp, device=pts.device, dtype=torch.float32)
+    render = torch.empty(B, C, H, W, device=pts.device, dtype=torch.float32)
+    existing = torch.empty(B, 1, H, W, device=pts.device, dtype=torch.float32)
+    nat.check(L.kb_splat_accum(_ptr(pts), _ptr(dat), B, N, C, None, float(dblFocal), float(dblBaseline), _ptr(zee),
+                               _ptr(acc), H, W, _stream()), "kb_splat_accum")
+    nat.check(L.kb_normalize(_ptr(acc), B, C, H, W, _ptr(render), _ptr(existing), _stream()), "kb_normalize")
+    return render, existing
+
+
 def fill_disocclusion(tensorInput, tensorDepth):
     """utils/common.py:833-937.  [B,C,H,W], [B,1,H,W] -> filled copy of the input."""
     _need_cuda(tensorInput, tensorDepth)

@@ -47,7 +47,47 @@ def default_zoom(W, H, dolly=False):
     return {'objectFrom': frm, 'objectTo': to}
 
 
-def scene_cloud(W=1024, H=768, seed=1234, focal=None, baseline=120.0, extra_points=0):
+def _standin_inpaint(pts, rgb, dep, W, H, focal, shift):
+    """A numpy stand-in for one process_inpaint pass (utils/common.py:47-81) WITHOUT the CNN: warp the grid
+    cloud by `shift`, find the disoccluded pixels of that view, give them the depth/colour of the farther of
+    their nearest valid row neighbours (what a good inpainter would hallucinate: background), and
+    back-project them into the reference frame.  Input generator only -- not part of any parity claim."""
+    x, y, z = pts[0].astype(np.float64) + shift[0], pts[1].astype(np.float64) + shift[1], pts[2].astype(np.float64) + shift[2]
+    ok = z > 1e-3
+    u = np.rint(focal * x / np.where(ok, z, 1.0) + W / 2.0 - 0.5).astype(np.int64)
+    v = np.rint(focal * y / np.where(ok, z, 1.0) + H / 2.0 - 0.5).astype(np.int64)
+    ok &= (u >= 0) & (u < W) & (v >= 0) & (v < H)
+    pix = (v * W + u)[ok]
+    idx = np.nonzero(ok)[0]
+    order = np.lexsort((z[idx], pix))
+    pix_s, idx_s = pix[order], idx[order]
+    first = np.ones(len(pix_s), bool)
+    first[1:] = pix_s[1:] != pix_s[:-1]
+    win = np.full(W * H, -1, np.int64)
+    win[pix_s[first]] = idx_s[first]
+    win = win.reshape(H, W)
+    hole = win < 0
+    # nearest valid neighbour to the left / right on the same row
+    cols = np.arange(W)[None, :].repeat(H, 0)
+    left = np.maximum.accumulate(np.where(hole, -1, cols), axis=1)
+    right = np.minimum.accumulate(np.where(hole, W, cols)[:, ::-1], axis=1)[:, ::-1]
+    rows = np.arange(H)[:, None].repeat(W, 1)
+    lw = np.where(left >= 0, win[rows, np.clip(left, 0, W - 1)], -1)
+    rw = np.where(right < W, win[rows, np.clip(right, 0, W - 1)], -1)
+    zl = np.where(lw >= 0, z[np.clip(lw, 0, None)], -np.inf)
+    zr = np.where(rw >= 0, z[np.clip(rw, 0, None)], -np.inf)
+    src = np.where(zl >= zr, lw, rw)
+    sel = hole & (src >= 0)
+    hv, hu = np.nonzero(sel)
+    s_idx = src[sel]
+    D = z[s_idx].astype(np.float32)
+    ul = (np.linspace(-0.5 * W + 0.5, 0.5 * W - 0.5, W, dtype=np.float32) * np.float32(1.0 / focal))
+    vl = (np.linspace(-0.5 * H + 0.5, 0.5 * H - 0.5, H, dtype=np.float32) * np.float32(1.0 / focal))
+    new_pts = np.stack([D * ul[hu], D * vl[hv], D], 0).astype(np.float32) - np.asarray(shift, np.float32)[:, None]
+    return new_pts, rgb[:, s_idx], D[None, :]
+
+
+def scene_cloud(W=1024, H=768, seed=1234, focal=None, baseline=120.0, extra_points=0, inpaint_standin=False):
     """A ready-to-render cloud in the layout process_kenburns keeps in objectCommon (numpy, CPU):
     points [3,N] (depth_to_points of depth = f*B/(disp+1e-7)), rgb [3,N] in [0,1], depth [1,N], plus the
     objectCommon scalars process_shift needs.  extra_points > 0 appends that many points resampled from the
@@ -71,6 +111,21 @@ def scene_cloud(W=1024, H=768, seed=1234, focal=None, baseline=120.0, extra_poin
         pts = np.concatenate([pts, ex], 1)
         rgb = np.concatenate([rgb, rgb[:, idx]], 1)
         dep = np.concatenate([dep, ex[2:3]], 1)
+    depthrange = cv2.minMaxLoc(depth[128:-128, 128:-128]) if (H > 256 and W > 256) else cv2.minMaxLoc(depth)
+    if inpaint_standin:
+        # the two extreme views of the default camera path, shift scaled by 1.1 like utils/common.py:218
+        from . import common as kb
+        cm = {'dblFocal': float(focal), 'dblBaseline': baseline, 'intWidth': W, 'intHeight': H,
+              'objectDepthrange': depthrange}
+        zoom = default_zoom(W, H)
+        st = {'dblSteps': [0.0, 1.0], 'objectFrom': zoom['objectFrom'], 'objectTo': zoom['objectTo'], 'dolly': False}
+        grid_pts, grid_rgb, grid_dep = pts[:, :W * H], rgb[:, :W * H], dep[:, :W * H]
+        for sh, _ in kb.kenburns_poses(st, cm):
+            shift = (sh.astype(np.float32) * np.float32(1.1)).astype(np.float64)
+            a, b, c = _standin_inpaint(grid_pts, grid_rgb, grid_dep, W, H, float(focal), shift)
+            pts = np.concatenate([pts, a], 1)
+            rgb = np.concatenate([rgb, b], 1)
+            dep = np.concatenate([dep, c], 1)
     mn, mx, mnl, mxl = cv2.minMaxLoc(depth[128:-128, 128:-128]) if (H > 256 and W > 256) else cv2.minMaxLoc(depth)
     common = {
         'dblFocal': float(focal), 'dblBaseline': baseline, 'intWidth': W, 'intHeight': H,

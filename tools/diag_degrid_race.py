@@ -13,7 +13,8 @@ sys.path.insert(0, ROOT)
 import oracle  # noqa: E402
 from oracle import refgpu  # noqa: E402
 from ken_burns_effect_b200.utils import common as kb  # noqa: E402
-from tests import helpers  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import kb_helpers as helpers  # noqa: E402
 
 OUT = os.path.join(ROOT, "gpurun_out", "golden")
 os.makedirs(OUT, exist_ok=True)
@@ -33,11 +34,11 @@ for (W, H, focal, extra) in [(64, 48, 32.0, 517), (256, 192, 128.0, 4099), (1024
         runs = []
         for rep in range(3):
             r_render, r_exist, r_zraw, r_zdeg, r_out = refgpu.render_pointcloud(tp, td, W, H, focal, 120, stages=True)
-            runs.append((r_render.cpu().numpy(), r_exist.cpu().numpy(), r_zdeg.cpu().numpy()))
+            runs.append((r_render.cpu().numpy(), r_exist.cpu().numpy(), r_zdeg.cpu().numpy(), r_out.cpu().numpy()))
         o_render, o_exist, o_zraw, o_zj = oracle.render_pointcloud(shifted[None], data[None], W, H, focal, 120, want_zee=True)
         s_render, s_exist, _, o_zs = oracle.render_pointcloud(shifted[None], data[None], W, H, focal, 120, degrid_mode=1, want_zee=True)
         m_render, m_exist, m_zraw, m_zdeg = kb.render_pointcloud(tp, td, W, H, focal, 120, return_zee=True)
-        rr, re_, rz = runs[0]
+        rr, re_, rz, rout = runs[0]          # every saved array comes from the SAME run of the reference
         info = dict(W=W, H=H, extra=extra, step=step,
                     zraw_bitexact_ref_vs_oracle=bool(np.array_equal(r_zraw.cpu().numpy().view(np.int32), o_zraw.view(np.int32))),
                     zraw_bitexact_ref_vs_mine=bool(torch.equal(r_zraw.view(torch.int32), m_zraw.view(torch.int32))),
@@ -55,5 +56,5 @@ for (W, H, focal, extra) in [(64, 48, 32.0, 517), (256, 192, 128.0, 4099), (1024
         if W <= 256:
             np.savez_compressed(os.path.join(OUT, f"ref_render_{W}x{H}_e{extra}_s{int(step)}.npz"),
                                 points=shifted.astype(np.float32), data=data.astype(np.float32), focal=focal, baseline=120,
-                                zee_raw=r_zraw.cpu().numpy(), zee_degrid=rz, out=r_out.cpu().numpy(),
+                                zee_raw=r_zraw.cpu().numpy(), zee_degrid=rz, out=rout,
                                 render=rr, existing=re_)
