@@ -1,0 +1,61 @@
+"""Semantics (VGG19-bn trunk) and Disparity (6-row GridNet) -- mirrors of models/disparity_estimation.py:82-198
+with identical constructors, forwards and state_dict keys."""
+import torch
+import torch.nn as nn
+import torchvision
+
+from .gridnet import Basic, add_grid, grid_forward, grid_name
+
+
+def _vgg19_bn_features():
+    """torchvision's VGG19-bn feature stack.  The reference asks for ImageNet weights
+    (disparity_estimation.py:86); they are used when torchvision can find them in the local hub cache and
+    silently replaced by the default initialisation when it cannot (no network in this environment).
+    The weights are not part of any released .tar checkpoint."""
+    try:
+        return torchvision.models.vgg19_bn(weights=torchvision.models.VGG19_BN_Weights.IMAGENET1K_V1).features.eval()
+    except Exception:
+        return torchvision.models.vgg19_bn(weights=None).features.eval()
+
+
+class Semantics(nn.Module):
+    def __init__(self):
+        super().__init__()
+        vgg = _vgg19_bn_features()
+        pool = lambda: nn.MaxPool2d(kernel_size=2, stride=2, ceil_mode=True)  # noqa: E731
+        # slices keep torchvision's indices as keys ("moduleVgg.3.7.weight"), disparity_estimation.py:88-105
+        self.moduleVgg = nn.Sequential(
+            vgg[0:3], vgg[3:6], pool(),
+            vgg[7:10], vgg[10:13], pool(),
+            vgg[14:17], vgg[17:20], vgg[20:23], vgg[23:26], pool(),
+            vgg[27:30], vgg[30:33], vgg[33:36], vgg[36:39], pool())
+
+    def forward(self, tensorInput):
+        # BGR -> RGB, ImageNet normalisation (disparity_estimation.py:108-116); done out of place
+        x = tensorInput[:, [2, 1, 0], :, :]
+        mean = x.new_tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+        std = x.new_tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+        return self.moduleVgg((x - mean) / std)
+
+
+class Disparity(nn.Module):
+    FEATURES = (32, 48, 64, 512, 512, 512)
+
+    def __init__(self):
+        super().__init__()
+        self.spectral_norm = False
+        self.moduleImage = nn.Conv2d(in_channels=3, out_channels=32, kernel_size=7, stride=2, padding=3)
+        self.moduleSemantics = nn.Conv2d(in_channels=512, out_channels=512, kernel_size=3, stride=1, padding=1)
+        add_grid(self, self.FEATURES)
+        self.moduleDisparity = Basic('conv-relu-conv', [32, 32, 1])
+
+    def forward(self, tensorImage, tensorSemantics):
+        m = self._modules
+        rows = [self.moduleImage(tensorImage)]
+        for r in range(1, len(self.FEATURES)):
+            nxt = m[grid_name(r - 1, 0, r, 0)](rows[r - 1])
+            if r == 3:
+                nxt = nxt + self.moduleSemantics(tensorSemantics)      # disparity_estimation.py:159
+            rows.append(nxt)
+        rows = grid_forward(self, rows)
+        return self.moduleDisparity(rows[0])

@@ -1,0 +1,86 @@
+"""Inpaint -- mirror of models/pointcloud_inpainting.py:83-236: context extractor, 68-channel point-cloud
+render, 4-row GridNet, colour and disparity heads; same constructor, forward signature, return dict and
+state_dict keys (so the released inpainting .tar loads unchanged)."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..utils import common as kb
+from .gridnet import Basic, add_grid, grid_forward, grid_name, sample_norm
+
+
+class Inpaint(nn.Module):
+    FEATURES = (32, 64, 128, 256)
+
+    def __init__(self):
+        super().__init__()
+        self.spectral_norm = False
+        self.moduleContext = nn.Sequential(
+            nn.Conv2d(in_channels=4, out_channels=64, kernel_size=3, stride=1, padding=1, bias=True),
+            nn.PReLU(num_parameters=64, init=0.25),
+            nn.Conv2d(in_channels=64, out_channels=64, kernel_size=3, stride=1, padding=1, bias=True),
+            nn.PReLU(num_parameters=64, init=0.25))
+        # image(3) :: disparity(1) :: context(64) :: mask(1)
+        self.moduleInput = Basic('conv-relu-conv', [3 + 1 + 64 + 1, 32, 32])
+        add_grid(self, self.FEATURES)
+        self.moduleImage = Basic('conv-relu-conv', [32, 32, 3])
+        self.moduleDisparity = Basic('conv-relu-conv', [32, 32, 1])
+
+    # -- models/pointcloud_inpainting.py:217-236 ------------------------------------------------------
+    def normalize_images_disp(self, tensorImage, tensorDisparity, not_normed=True):
+        """not_normed=True: store per-sample mean/std on the module and return normalised copies;
+        False: undo the normalisation with the stored statistics (the module is stateful, like the reference)."""
+        if not_normed:
+            self.tensorMean, self.tensorStd = sample_norm(tensorImage, tensorDisparity)
+            img = (tensorImage - self.tensorMean[0]) / (self.tensorStd[0] + 0.0000001)
+            disp = (tensorDisparity - self.tensorMean[1]) / (self.tensorStd[1] + 0.0000001)
+            return img, disp
+        img = tensorImage * (self.tensorStd[0] + 0.0000001) + self.tensorMean[0]
+        disp = tensorDisparity * (self.tensorStd[1] + 0.0000001) + self.tensorMean[1]
+        return img, disp
+
+    def _column0(self, tensorData, tensorMasks):
+        m = self._modules
+        rows = [self.moduleInput(torch.cat([tensorData, tensorMasks], 1))]
+        for r in range(1, len(self.FEATURES)):
+            rows.append(m[grid_name(r - 1, 0, r, 0)](rows[r - 1]))
+        return rows
+
+    # -- models/pointcloud_inpainting.py:122-182 ------------------------------------------------------
+    def forward(self, tensorMasks, tensorImage=None, tensorDisparity=None, tensorData=None, tensorContext=None):
+        if tensorImage is not None and tensorContext is None:
+            tensorImage, tensorDisparity = self.normalize_images_disp(tensorImage, tensorDisparity, not_normed=True)
+        if tensorData is None and tensorContext is not None:
+            tensorData = torch.cat([tensorImage, tensorDisparity, tensorContext], 1)
+        elif tensorData is None:
+            tensorContext = self.moduleContext(torch.cat([tensorImage, tensorDisparity], 1))
+            tensorData = torch.cat([tensorImage, tensorDisparity, tensorContext], 1)
+
+        rows = grid_forward(self, self._column0(tensorData, tensorMasks))
+        img, disp = self.normalize_images_disp(self.moduleImage(rows[0]), self.moduleDisparity(rows[0]), not_normed=False)
+        return {
+            'tensorExisting': tensorMasks,
+            'tensorImage': img.clamp(0.0, 1.0) if self.training == False else img,  # noqa: E712
+            'tensorDisparity': F.threshold(input=disp, threshold=0.0, value=0.0),
+        }
+
+    # -- models/pointcloud_inpainting.py:185-213 ------------------------------------------------------
+    def _render_inputs(self, tensorImage, tensorDisparity, tensorShift, objectCommon, dblFocal):
+        if dblFocal is None:
+            dblFocal = objectCommon['dblFocal']
+        assert tensorImage.shape[0] == 1, 'Please process one image at a time.'
+        depth = (dblFocal * objectCommon['dblBaseline']) / (tensorDisparity + 0.0000001)
+        valid = (kb.spatial_filter(tensorDisparity / tensorDisparity.max(), 'laplacian').abs() < 0.03).float()
+        points = kb.depth_to_points(depth * valid, dblFocal).view(1, 3, -1)
+        img, disp = self.normalize_images_disp(tensorImage, tensorDisparity, not_normed=True)
+        context = self.moduleContext(torch.cat([img, disp], 1))
+        render, existing = kb.render_pointcloud(points + tensorShift, torch.cat([img, disp, context], 1).view(1, 68, -1),
+                                                objectCommon['intWidth'], objectCommon['intHeight'], dblFocal,
+                                                objectCommon['dblBaseline'])
+        existing = (existing > 0.0).float()
+        existing = existing * kb.spatial_filter(existing, 'median-5')
+        return render * existing, existing
+
+    def pointcloud_inpainting(self, tensorImage, tensorDisparity, tensorShift, objectCommon, dblFocal=None):
+        render, existing = self._render_inputs(tensorImage, tensorDisparity, tensorShift, objectCommon, dblFocal)
+        return self.forward(tensorData=render, tensorMasks=existing)

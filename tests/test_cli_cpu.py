@@ -1,0 +1,54 @@
+"""CPU: kbe.py option parsing, image preparation and crop-window rules (kbe.py:42-169 of the reference)."""
+import importlib.util
+import os
+
+import cv2
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+spec = importlib.util.spec_from_file_location("kbe_cli", os.path.join(ROOT, "kbe.py"))
+kbe = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(kbe)
+
+
+def test_defaults_match_reference():
+    cfg = kbe.parse([])
+    assert cfg['input_path'] == 'images/doublestrike.jpg' and cfg['output_path'] == 'images/kbe'
+    assert cfg['inpaint_path'] == './models/trained/inpainting-color.tar'
+    assert cfg['estim_path'] == './models/trained/disparity-estimation-no-mask.tar'
+    assert cfg['frames'] == 75 and not cfg['dolly'] and not cfg['partial']
+
+
+def test_flags():
+    cfg = kbe.parse(['--in', 'a.png', '--out', 'o', '--dolly', '--write-frames', '--startU', '10', '--endH', '40',
+                     '--partial-conv', '--frames', '150', '--2d', '--pretrained-refine'])
+    assert cfg['input_path'] == 'a.png' and cfg['dolly'] and cfg['output_frames'] and cfg['startU'] == 10
+    assert cfg['endH'] == 40 and cfg['partial'] and cfg['frames'] == 150 and cfg['d2'] and cfg['pretrained_refine']
+
+
+def test_default_windows_1024x768():
+    z = kbe.crop_windows(kbe.parse([]), 1024, 768)
+    assert z['objectFrom'] == {'dblCenterU': 1024 / 2.15, 'dblCenterV': 768 / 2.15, 'intCropWidth': 921, 'intCropHeight': 691}
+    assert z['objectTo'] == {'dblCenterU': 1024 / 1.85, 'dblCenterV': 768 / 1.85, 'intCropWidth': 870, 'intCropHeight': 652}
+    z = kbe.crop_windows(kbe.parse(['--dolly']), 1024, 768)
+    assert z['objectFrom']['intCropWidth'] == 819 and z['objectTo']['intCropWidth'] == 307 and z['objectTo']['intCropHeight'] == 230
+
+
+def test_window_asserts():
+    cfg = kbe.parse(['--startU', '10', '--startV', '10', '--startW', '400', '--startH', '300', '--endU', '512', '--endV',
+                     '384', '--endW', '100', '--endH', '80'])
+    with pytest.raises(AssertionError):
+        kbe.crop_windows(cfg, 1024, 768)
+
+
+def test_load_image_crops_to_multiple_of_4(tmp_path):
+    img = np.random.default_rng(0).integers(0, 256, (37, 50, 3), dtype=np.uint8)
+    p = str(tmp_path / "x.png")
+    cv2.imwrite(p, img)
+    t = kbe.load_image(p, False)
+    assert t.shape == (3, 36, 48)
+    ref = (torch.from_numpy(img[:36, :48]).permute(2, 0, 1).float() / 255 - 0.5) / 0.5
+    assert torch.equal(t, ref)
+    assert float(((t + 1) / 2).min()) >= 0.0

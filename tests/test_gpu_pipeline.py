@@ -1,0 +1,84 @@
+"""GPU: the whole Pipeline (depth CNNs -> point cloud -> two inpainting passes -> fused frame loop) with
+random weights on a synthetic image, against an oracle pipeline assembled from the CPU pieces that are each
+pinned to the reference: the nn.Module mirrors on CPU fp32 (tests/test_models_cpu.py) and the C oracle for
+every kernel (tests/test_oracle_golden.py).  Random-weight CNNs make chaotic disparities, so discrete
+decisions (laplacian validity, holes) can flip on 1e-6 differences between cuDNN and CPU convolutions: the
+bar here is statistical (mean abs byte difference), the exact bars live in the per-stage tests."""
+import numpy as np
+import pytest
+import torch
+
+import kb_helpers
+import oracle
+from ken_burns_effect_b200.utils import common as kb
+from ken_burns_effect_b200.utils import synthetic
+from ken_burns_effect_b200.utils.pipeline import Pipeline
+
+pytestmark = pytest.mark.gpu
+
+
+def test_pipeline_dolly_runs_and_matches_frame_oracle():
+    """Dolly mode (no inpainting stage): CNN depth on the GPU, then frames; the frame loop is checked
+    against the oracle on the very cloud the GPU pipeline produced (exact bar: <=1 per byte)."""
+    torch.manual_seed(0)
+    W, H = 384, 320
+    img, _ = synthetic.synthetic_scene(W, H, seed=5)
+    t = torch.from_numpy(img).permute(2, 0, 1).float().div(255).view(1, 3, H, W)
+    pipe = Pipeline(model_paths=None, dolly=True, frames=5)
+    zoom = synthetic.default_zoom(W, H, dolly=True)
+    frames = pipe(t, zoom)
+    assert len(frames) == 5 and frames[0].shape == (H, W, 3)
+    oc = pipe.objectCommon
+    st = {'dblSteps': np.linspace(0, 1, 5).tolist(), 'objectFrom': zoom['objectFrom'], 'objectTo': zoom['objectTo'], 'dolly': True}
+    poses = kb.kenburns_poses(st, oc)
+    pts = oc['tensorInpaPoints'][0].cpu().numpy()
+    data = np.concatenate([oc['tensorInpaImage'][0].cpu().numpy(), oc['tensorInpaDepth'][0].cpu().numpy()], 0)
+    cw = max(zoom['objectFrom']['intCropWidth'], zoom['objectTo']['intCropWidth'])
+    ch = max(zoom['objectFrom']['intCropHeight'], zoom['objectTo']['intCropHeight'])
+    oracle.set_threads(0)
+    for i, (sh, f) in enumerate(poses):
+        ref = oracle.frame(oracle.shift_points(pts, sh), data, W, H, f, oc['dblBaseline'], cw, ch)
+        d = np.abs(frames[i].astype(np.int16) - ref.astype(np.int16))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-3
+
+
+def test_pipeline_with_inpainting_grows_the_cloud():
+    torch.manual_seed(1)
+    W, H = 384, 320
+    img, _ = synthetic.synthetic_scene(W, H, seed=6)
+    t = torch.from_numpy(img).permute(2, 0, 1).float().div(255).view(1, 3, H, W)
+    pipe = Pipeline(model_paths=None, dolly=False, frames=3)
+    frames = pipe(t, synthetic.default_zoom(W, H))
+    oc = pipe.objectCommon
+    n = oc['tensorInpaPoints'].shape[-1]
+    assert n >= W * H and oc['tensorInpaImage'].shape[-1] == n and oc['tensorInpaDepth'].shape[-1] == n
+    assert len(frames) == 3 and frames[0].dtype == np.uint8 and np.isfinite(np.stack(frames)).all()
+
+
+def test_pointcloud_inpainting_render_inputs_vs_oracle():
+    """The 68-channel render + mask post-processing of Inpaint.pointcloud_inpainting
+    (models/pointcloud_inpainting.py:192-210) against the CPU oracle, using the GPU context features."""
+    from ken_burns_effect_b200.models.pointcloud_inpainting import Inpaint
+    torch.manual_seed(2)
+    W, H, focal = 256, 192, 128.0
+    img, disp = synthetic.synthetic_scene(W, H, seed=7)
+    ti = torch.from_numpy(img[:, :, ::-1].copy()).permute(2, 0, 1).float().div(255).view(1, 3, H, W).cuda()
+    td = torch.from_numpy(disp).view(1, 1, H, W).cuda()
+    net = kb_helpers.deterministic_state(Inpaint()).cuda().eval()
+    shift = torch.tensor([8.0, -5.0, -20.0], device="cuda").view(1, 3, 1)
+    oc = {'dblFocal': focal, 'dblBaseline': 120, 'intWidth': W, 'intHeight': H}
+    with torch.no_grad():
+        render, existing = net._render_inputs(ti, td, shift, oc, None)
+        # oracle on the same inputs
+        depth = (focal * 120) / (td + 0.0000001)
+        valid = (kb.spatial_filter(td / td.max(), 'laplacian').abs() < 0.03).float()
+        pts = (kb.depth_to_points(depth * valid, focal).view(1, 3, -1) + shift).cpu().numpy()
+        im, dn = net.normalize_images_disp(ti, td, not_normed=True)
+        ctx = net.moduleContext(torch.cat([im, dn], 1))
+        data = torch.cat([im, dn, ctx], 1).view(1, 68, -1).cpu().numpy()
+    oracle.set_threads(0)
+    o_render, o_exist = oracle.render_pointcloud(pts, data, W, H, focal, 120)
+    o_mask = (o_exist > 0).astype(np.float32)
+    o_mask = o_mask * oracle.median5_binary(o_mask)
+    assert np.array_equal(existing.cpu().numpy(), o_mask)
+    assert kb_helpers.rel_l2(render.cpu().numpy(), o_render * o_mask) < 2e-5
