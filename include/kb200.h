@@ -117,6 +117,63 @@ size_t kb_frames_workspace_bytes(const kb_frame_params *p, int K);
 int kb_render_frames(const float *xyz, const float *rgbd, long N, const kb_pose *poses_host, int K,
                      const kb_frame_params *p, void *workspace, uint8_t *frames, kb_stream_t stream);
 
+/* ---- the conv stacks: every nn.Conv2d of models/disparity_estimation.py, models/disparity_refinement*.py,
+ *      models/pointcloud_inpainting.py and what surrounds it (bias, PReLU, residual / skip sums) ------------
+ * Activations are NHWC fp32 ("pixel stride" = floats between consecutive pixels, a multiple of 4, which lets a
+ * tensor be a channel slice of a wider concat buffer -- torch.cat of the reference, disparity_refinement.py:100-104).
+ * Arithmetic: TF32 operands, fp32 accumulation on the tcgen05 tensor cores (what cuDNN does for the reference under
+ * PyTorch's default torch.backends.cudnn.allow_tf32=True on this GPU). */
+
+/* Number of floats kb_conv_pack_weights writes for a [Cout,Cin,k,k] filter. */
+long kb_conv_packed_floats(int Cout, int Cin, int ksize);
+/* nn.Conv2d.weight [Cout,Cin,k,k] (device) -> the layout kb_conv2d reads, rounded to TF32.  out_scale: optional
+ * [Cout] factor folded into the filter (eval-mode BatchNorm of the VGG trunk, disparity_estimation.py:86-105). */
+int kb_conv_pack_weights(const float *w_oihw, int Cout, int Cin, int ksize, const float *out_scale, float *packed,
+                         kb_stream_t stream);
+
+typedef struct kb_conv_out {
+  float *ptr;            /* [N,Ho,Wo,pixel_stride] */
+  long pixel_stride;     /* floats, multiple of 4, >= round_up(Cout,4); channels Cout..round_up(Cout,4) are written as 0 */
+  const float *slope;    /* per-channel PReLU weight applied to THIS output (NULL: none) -- the activation that
+                            precedes the consumer's convolution ('relu-conv-relu-conv', pointcloud_inpainting.py:12-17) */
+  int round_tf32;        /* 1: round to TF32 (value is only ever read by another convolution) */
+  int _pad;
+} kb_conv_out;
+
+typedef struct kb_conv_args {
+  const float *x;        /* [N,H,W,x_stride] */
+  int N, H, W, Cin;
+  long x_stride;
+  const float *w_packed; /* kb_conv_pack_weights output */
+  const float *bias;     /* [Cout] or NULL */
+  int Cout, ksize, stride, pad;   /* ksize 1..7, stride 1 or 2 */
+  const float *res;      /* optional tensor added before the outputs' PReLUs (residual / GridNet skip sum), [N,Ho,Wo,res_stride] */
+  long res_stride;
+  int n_out;             /* 1..3 */
+  kb_conv_out out[3];
+  int out_H, out_W;      /* 0 = the convolution's own output size; smaller: only the top-left out_H x out_W pixels exist in
+                            out/res (the reference crops an up-sampled odd-sized map with F.pad(-1), pointcloud_inpainting.py:154) */
+  int tile_w;            /* 0 = auto; output tile is tile_w x (128/tile_w) pixels */
+  int n_block;           /* 0 = auto; output channels per CTA (multiple of 16, <= 256) */
+  int stages;            /* 0 = auto; shared-memory pipeline depth */
+} kb_conv_args;
+
+/* out_o = prelu_o(conv(x, w) + bias + res)   for o < n_out;  one launch. */
+int kb_conv2d(const kb_conv_args *args, kb_stream_t stream);
+
+/* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) followed by the block's first PReLU
+ * (models/pointcloud_inpainting.py:70-72); the output may be cropped to Ho x Wo (the reference's F.pad(-1), :154-155). */
+int kb_upsample2x_prelu(const float *x, long x_stride, int N, int H, int W, int C, const float *slope, float *y, long y_stride,
+                        int Ho, int Wo, int round_tf32, kb_stream_t stream);
+/* y = prelu(x) per channel (slope NULL: strided copy). */
+int kb_prelu_nhwc(const float *x, long x_stride, long pixels, int C, const float *slope, float *y, long y_stride, int round_tf32,
+                  kb_stream_t stream);
+/* nn.MaxPool2d(2, 2, ceil_mode=True), models/disparity_estimation.py:90. */
+int kb_maxpool2_ceil(const float *x, long x_stride, int N, int H, int W, int C, float *y, long y_stride, kb_stream_t stream);
+/* Layout changes at the module boundary: y_nhwc = (x_nchw - sub) * mul ; y_nchw = x_nhwc * mul + add. */
+int kb_nchw_to_nhwc(const float *x, int N, int C, int H, int W, float *y, long y_stride, float sub, float mul, kb_stream_t stream);
+int kb_nhwc_to_nchw(const float *x, long x_stride, int N, int C, int H, int W, float *y, float mul, float add, kb_stream_t stream);
+
 /* ---- measurement hooks (bench.py) ---------------------------------------------------------------- */
 /* Stages of kb_render_frames, in launch order: 0 memset(accumulators) 1 init(z-buffer + resize tables)
  * 2 splat_min 3 degrid 4 splat_accum 5 resolve (normalise+quantise+hole list) 6 fill 7 crop+resize. */

@@ -27,6 +27,17 @@ class KBFrameParams(ctypes.Structure):
     _fields_ = [("H", c_int), ("W", c_int), ("crop_w", c_int), ("crop_h", c_int), ("baseline", c_double)]
 
 
+class KBConvOut(ctypes.Structure):
+    _fields_ = [("ptr", c_void), ("pixel_stride", c_long), ("slope", c_void), ("round_tf32", c_int), ("_pad", c_int)]
+
+
+class KBConvArgs(ctypes.Structure):
+    _fields_ = [("x", c_void), ("N", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("x_stride", c_long),
+                ("w_packed", c_void), ("bias", c_void), ("Cout", c_int), ("ksize", c_int), ("stride", c_int),
+                ("pad", c_int), ("res", c_void), ("res_stride", c_long), ("n_out", c_int), ("out", KBConvOut * 3),
+                ("out_H", c_int), ("out_W", c_int), ("tile_w", c_int), ("n_block", c_int), ("stages", c_int)]
+
+
 # name -> (restype, argtypes); must list every symbol include/kb200.h declares (tests/test_abi.py checks).
 SIGNATURES = {
     "kb_version": (c_int, []),
@@ -47,6 +58,15 @@ SIGNATURES = {
     "kb_frames_workspace_bytes": (c_size_t, [ctypes.POINTER(KBFrameParams), c_int]),
     "kb_render_frames": (c_int, [c_void, c_void, c_long, ctypes.POINTER(KBPose), c_int,
                                  ctypes.POINTER(KBFrameParams), c_void, c_void, c_void]),
+    "kb_conv_packed_floats": (c_long, [c_int, c_int, c_int]),
+    "kb_conv_pack_weights": (c_int, [c_void, c_int, c_int, c_int, c_void, c_void, c_void]),
+    "kb_conv2d": (c_int, [ctypes.POINTER(KBConvArgs), c_void]),
+    "kb_upsample2x_prelu": (c_int, [c_void, c_long, c_int, c_int, c_int, c_int, c_void, c_void, c_long, c_int, c_int,
+                                    c_int, c_void]),
+    "kb_prelu_nhwc": (c_int, [c_void, c_long, c_long, c_int, c_void, c_void, c_long, c_int, c_void]),
+    "kb_maxpool2_ceil": (c_int, [c_void, c_long, c_int, c_int, c_int, c_int, c_void, c_long, c_void]),
+    "kb_nchw_to_nhwc": (c_int, [c_void, c_int, c_int, c_int, c_int, c_void, c_long, ctypes.c_float, ctypes.c_float, c_void]),
+    "kb_nhwc_to_nchw": (c_int, [c_void, c_long, c_int, c_int, c_int, c_int, c_void, ctypes.c_float, ctypes.c_float, c_void]),
     "kb_profile_enable": (c_int, [c_int]),
     "kb_profile_read": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]),
 }

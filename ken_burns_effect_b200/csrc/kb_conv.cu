@@ -1,0 +1,650 @@
+// kb_conv.cu -- 2-D convolution of the reference's conv stacks as an implicit GEMM on the 5th-gen tensor cores.
+//
+// Reference: every nn.Conv2d of models/disparity_estimation.py, models/disparity_refinement*.py,
+// models/pointcloud_inpainting.py (3x3 stride 1/2, 1x1 shortcuts, the 7x7 stride-2 stem) together with
+// what surrounds it there: bias, the per-channel PReLU that follows (or precedes the next conv), the
+// residual / skip sum of the GridNet (pointcloud_inpainting.py:141-172).  cuDNN runs these as fp32 NCHW
+// convolutions plus separate elementwise kernels; PyTorch's default on this GPU lets cuDNN use TF32.
+//
+// B200 design (one CTA = one tile of 128 output pixels x Npad output channels):
+//   * activations are NHWC fp32 in HBM.  For every filter tap (r,s) and every 32-channel slice the A
+//     operand of the GEMM is the input tile shifted by the tap -- one TMA box load {32 ch, tile_w, tile_h}
+//     at (x0*stride + s - pad, y0*stride + r - pad); TMA zero-fills everything outside the image, which is
+//     the convolution's zero padding, and its traversal stride is the convolution stride.  No im2col
+//     buffer, no index arithmetic in the kernel.
+//   * weights are pre-packed per (tap, 32-channel slice) as K-major [Cout][32] panels, TMA-loaded next to A.
+//   * both operands land in shared memory in the 128-byte swizzled K-major layout that tcgen05.mma reads
+//     through shared-memory descriptors; the accumulator (128 lanes x Npad fp32 columns) lives in TMEM.
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2..5 = epilogue:
+//     tcgen05.ld the accumulator, + bias, + residual, then up to three outputs, each optionally passed
+//     through the next layer's PReLU, so that "PReLU -> conv" chains never need a separate elementwise pass.
+//   * a ring of `stages` shared-memory slots with full/empty mbarriers decouples TMA from the tensor pipe;
+//     small-N layers fit two CTAs per SM so one CTA's epilogue overlaps the other's main loop.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "kb_common.cuh"
+
+namespace kb {
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], tf32 inputs, fp32 accumulate; issued by ONE thread for the whole CTA.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive when every MMA issued so far by this thread has finished reading smem / writing TMEM.
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread l of the warp receives row (lane base + l).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte swizzled operand tile whose rows are 128 bytes: 8-row groups are 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) /* LBO (unused with swizzle) */ |
+         (64ull << 32) /* SBO = 1024 B */ | (1ull << 46) /* descriptor version: sm_100 */ | (2ull << 61) /* SWIZZLE_128B */;
+}
+
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// ---- kernel ------------------------------------------------------------------------------------------------
+constexpr int kTileM = 128;            // output pixels per CTA = UMMA M
+constexpr int kChunk = 32;             // input channels per K step (32 fp32 = one 128-byte swizzle row)
+constexpr int kABytes = kTileM * kChunk * 4;
+constexpr int kConvThreads = 192;      // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kMaxOut = 3;
+
+struct ConvOut {
+  float *ptr;
+  long stride;          // floats per pixel
+  const float *slope;   // per-channel PReLU applied to this output (nullptr = identity)
+  int round_tf32;       // round to TF32 (the value only feeds convolutions)
+};
+
+struct ConvKernelParams {
+  int Ho, Wo;           // stored output size (possibly cropped)
+  int tile_w, tile_h, tiles_x, tiles_y;
+  int chunks, ksize, stride, pad;
+  int Cout, Cout4;      // real output channels, and rounded up to 4 (allocated)
+  int Npad;             // UMMA N of this launch
+  int stages;
+  uint32_t tmem_cols;
+  const float *bias;
+  const float *res;
+  long res_stride;
+  int n_out;
+  ConvOut out[kMaxOut];
+};
+
+__global__ void __launch_bounds__(kConvThreads) k_conv_tf32(const __grid_constant__ CUtensorMap map_a,
+                                                            const __grid_constant__ CUtensorMap map_b,
+                                                            const ConvKernelParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages][A 16 KB | B Npad*128] then barriers
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_bytes = p.Npad * kChunk * 4;
+  const int stage_bytes = kABytes + b_bytes;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t *empty = full + p.stages;
+  uint64_t *acc_full = empty + p.stages;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // tile -> (image, y0, x0)
+  int t = blockIdx.x;
+  const int tx = t % p.tiles_x;
+  t /= p.tiles_x;
+  const int ty = t % p.tiles_y;
+  const int img = t / p.tiles_y;
+  const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
+  const int n0 = blockIdx.y * p.Npad;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int taps = p.ksize * p.ksize;
+  const int J = taps * p.chunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int j = 0; j < J; ++j) {
+        const int s = j % p.stages;
+        const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
+        mbar_wait(empty + s, ph ^ 1u);
+        uint8_t *a_dst = smem + (size_t)s * stage_bytes;
+        uint8_t *b_dst = a_dst + kABytes;
+        const int tap = j / p.chunks, ck = j - tap * p.chunks;
+        const int r = tap / p.ksize, q = tap - r * p.ksize;
+        mbar_expect_tx(full + s, (uint32_t)stage_bytes);
+        tma_load_4d(&map_a, full + s, a_dst, ck * kChunk, x0 * p.stride + q - p.pad, y0 * p.stride + r - p.pad, img);
+        tma_load_3d(&map_b, full + s, b_dst, 0, n0, j);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = (1u << 4) /* D fp32 */ | (2u << 7) /* A tf32 */ | (2u << 10) /* B tf32 */ |
+                             ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      for (int j = 0; j < J; ++j) {
+        const int s = j % p.stages;
+        const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
+        mbar_wait(full + s, ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t b_addr = a_addr + kABytes;
+        const uint64_t da = umma_desc_sw128(a_addr), db = umma_desc_sw128(b_addr);
+#pragma unroll
+        for (int k = 0; k < kChunk / 8; ++k)   // UMMA K = 8 tf32 = 32 bytes: advance the start address inside the swizzle row
+          umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (j | k) != 0);
+        umma_commit(empty + s);                // slot reusable once these MMAs have read it
+      }
+      umma_commit(acc_full);                   // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
+    const int q = warp & 3;
+    const int m = q * 32 + lane;               // accumulator row = pixel of the tile
+    const int py = m / p.tile_w, px = m - py * p.tile_w;
+    const int oy = y0 + py, ox = x0 + px;
+    const bool inside = (oy < p.Ho) & (ox < p.Wo);
+    const long pix = ((long)img * p.Ho + oy) * p.Wo + ox;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c0 = 0; c0 < p.Npad; c0 += 16) {
+      if (n0 + c0 >= p.Cout4) break;           // warp-uniform
+      float v[16];
+      tmem_ld16(taddr + (uint32_t)c0, v);
+      if (!inside) continue;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int c = n0 + c0 + 4 * g;
+        if (c >= p.Cout4) break;
+        float4 a = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        float bb[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.bias) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (c + e < p.Cout) bb[e] = __ldg(p.bias + c + e);
+        }
+        a.x += bb[0]; a.y += bb[1]; a.z += bb[2]; a.w += bb[3];
+        if (p.res) {
+          const float4 rr = *reinterpret_cast<const float4 *>(p.res + pix * p.res_stride + c);
+          a.x += rr.x; a.y += rr.y; a.z += rr.z; a.w += rr.w;
+        }
+        if (c + 1 >= p.Cout) a.y = 0.f;       // keep the padding channels of the allocation at zero
+        if (c + 2 >= p.Cout) a.z = 0.f;
+        if (c + 3 >= p.Cout) a.w = 0.f;
+#pragma unroll
+        for (int o = 0; o < kMaxOut; ++o) {
+          if (o >= p.n_out) break;
+          float4 w = a;
+          if (p.out[o].slope) {
+            float sl[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (c + e < p.Cout) sl[e] = __ldg(p.out[o].slope + c + e);
+            w.x = w.x > 0.f ? w.x : w.x * sl[0];
+            w.y = w.y > 0.f ? w.y : w.y * sl[1];
+            w.z = w.z > 0.f ? w.z : w.z * sl[2];
+            w.w = w.w > 0.f ? w.w : w.w * sl[3];
+          }
+          if (p.out[o].round_tf32) {
+            w.x = round_tf32(w.x); w.y = round_tf32(w.y); w.z = round_tf32(w.z); w.w = round_tf32(w.w);
+          }
+          *reinterpret_cast<float4 *>(p.out[o].ptr + pix * p.out[o].stride + c) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ---- weight packing: OIHW fp32 -> [tap][chunk][Cout_pad16][32] fp32 rounded to TF32 ------------------------
+__global__ void __launch_bounds__(256) k_pack_weights(const float *__restrict__ w, int Cout, int Cin, int ksize, int chunks,
+                                                      int Cout_pad, const float *__restrict__ out_scale, float *__restrict__ dst,
+                                                      long total) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ci = (int)(i % kChunk);
+  long r = i / kChunk;
+  const int o = (int)(r % Cout_pad);
+  r /= Cout_pad;
+  const int ck = (int)(r % chunks);
+  const int tap = (int)(r / chunks);
+  const int c = ck * kChunk + ci;
+  float v = 0.f;
+  if (o < Cout && c < Cin) {
+    v = w[((long)o * Cin + c) * ksize * ksize + tap];
+    if (out_scale) v *= out_scale[o];
+  }
+  dst[i] = round_tf32(v);
+}
+
+// ---- elementwise companions of the conv stacks (NHWC) ---------------------------------------------------------
+// bilinear x2 (align_corners=False) followed by the per-channel PReLU of the Upsample block
+// (models/pointcloud_inpainting.py:70-72); output optionally cropped to (Ho, Wo) <= (2H, 2W).
+__global__ void __launch_bounds__(256) k_upsample2x_prelu(const float *__restrict__ x, long xs, int H, int W, int C4,
+                                                          const float *__restrict__ slope, int C, float *__restrict__ y, long ys,
+                                                          int Ho, int Wo, int round, long total) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cg = (int)(i % C4);
+  long r = i / C4;
+  const int ox = (int)(r % Wo);
+  r /= Wo;
+  const int oy = (int)(r % Ho);
+  const int n = (int)(r / Ho);
+  // src = (dst + 0.5) / 2 - 0.5, clamped at 0 (PyTorch area_pixel_compute_source_index, align_corners=False)
+  const float sx = fmaxf(__fmaf_rn((float)ox + 0.5f, 0.5f, -0.5f), 0.f), sy = fmaxf(__fmaf_rn((float)oy + 0.5f, 0.5f, -0.5f), 0.f);
+  const int x0 = (int)sx, y0 = (int)sy;
+  const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+  const float lx = sx - (float)x0, ly = sy - (float)y0;
+  const float hx = 1.f - lx, hy = 1.f - ly;
+  const float *b = x + (long)n * H * W * xs + 4 * cg;
+  const float4 p00 = *reinterpret_cast<const float4 *>(b + ((long)y0 * W + x0) * xs);
+  const float4 p01 = *reinterpret_cast<const float4 *>(b + ((long)y0 * W + x1) * xs);
+  const float4 p10 = *reinterpret_cast<const float4 *>(b + ((long)y1 * W + x0) * xs);
+  const float4 p11 = *reinterpret_cast<const float4 *>(b + ((long)y1 * W + x1) * xs);
+  float o[4];
+  const float a00[4] = {p00.x, p00.y, p00.z, p00.w}, a01[4] = {p01.x, p01.y, p01.z, p01.w};
+  const float a10[4] = {p10.x, p10.y, p10.z, p10.w}, a11[4] = {p11.x, p11.y, p11.z, p11.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    // same association as ATen's upsample_bilinear2d: hy*(hx*p00 + lx*p01) + ly*(hx*p10 + lx*p11)
+    float v = hy * (hx * a00[e] + lx * a01[e]) + ly * (hx * a10[e] + lx * a11[e]);
+    const int c = 4 * cg + e;
+    if (slope && c < C) v = v > 0.f ? v : v * __ldg(slope + c);
+    if (c >= C) v = 0.f;
+    o[e] = round ? round_tf32(v) : v;
+  }
+  *reinterpret_cast<float4 *>(y + (((long)n * Ho + oy) * Wo + ox) * ys + 4 * cg) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// y = prelu(x) (slope per channel; nullptr = copy), NHWC with independent pixel strides.
+__global__ void __launch_bounds__(256) k_prelu_nhwc(const float *__restrict__ x, long xs, const float *__restrict__ slope, int C,
+                                                    int C4, float *__restrict__ y, long ys, int round, long total) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cg = (int)(i % C4);
+  const long pix = i / C4;
+  const float4 v = *reinterpret_cast<const float4 *>(x + pix * xs + 4 * cg);
+  float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = 4 * cg + e;
+    if (slope && c < C) a[e] = a[e] > 0.f ? a[e] : a[e] * __ldg(slope + c);
+    if (c >= C) a[e] = 0.f;
+    if (round) a[e] = round_tf32(a[e]);
+  }
+  *reinterpret_cast<float4 *>(y + pix * ys + 4 * cg) = make_float4(a[0], a[1], a[2], a[3]);
+}
+
+// 2x2 max-pool, stride 2, ceil_mode=True (models/disparity_estimation.py:90), NHWC.
+__global__ void __launch_bounds__(256) k_maxpool2_ceil(const float *__restrict__ x, long xs, int H, int W, int C4,
+                                                       float *__restrict__ y, long ys, int Ho, int Wo, long total) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cg = (int)(i % C4);
+  long r = i / C4;
+  const int ox = (int)(r % Wo);
+  r /= Wo;
+  const int oy = (int)(r % Ho);
+  const int n = (int)(r / Ho);
+  const float *b = x + (long)n * H * W * xs + 4 * cg;
+  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  for (int dy = 0; dy < 2; ++dy)
+    for (int dx = 0; dx < 2; ++dx) {
+      const int iy = 2 * oy + dy, ix = 2 * ox + dx;
+      if (iy >= H || ix >= W) continue;
+      const float4 v = *reinterpret_cast<const float4 *>(b + ((long)iy * W + ix) * xs);
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+  *reinterpret_cast<float4 *>(y + (((long)n * Ho + oy) * Wo + ox) * ys + 4 * cg) = m;
+}
+
+// NCHW [N,C,H,W] -> NHWC with pixel stride ys (>= C, channels beyond C zeroed up to C4*4), optional affine
+// per-tensor (x - sub) * mul used for the per-sample normalisation of Refine / Inpaint.
+__global__ void __launch_bounds__(256) k_nchw_to_nhwc(const float *__restrict__ x, int C, long HW, float *__restrict__ y, long ys,
+                                                      int C4, float sub, float mul, long total) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long pix = i % HW;          // consecutive threads -> consecutive pixels: coalesced plane reads
+  long r = i / HW;
+  const int cg = (int)(r % C4);
+  const int n = (int)(r / C4);
+  float a[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = 4 * cg + e;
+    a[e] = c < C ? (x[((long)n * C + c) * HW + pix] - sub) * mul : 0.f;
+  }
+  *reinterpret_cast<float4 *>(y + ((long)n * HW + pix) * ys + 4 * cg) = make_float4(a[0], a[1], a[2], a[3]);
+}
+
+// NHWC (pixel stride xs, channel offset applied by the caller) -> NCHW [N,C,H,W], y = x * mul + add.
+__global__ void __launch_bounds__(256) k_nhwc_to_nchw(const float *__restrict__ x, long xs, int C, long HW, float *__restrict__ y,
+                                                      float mul, float add, long total) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long pix = i % HW;
+  long r = i / HW;
+  const int c = (int)(r % C);
+  const int n = (int)(r / C);
+  y[i] = x[((long)n * HW + pix) * xs + c] * mul + add;
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+static int pow2_at_least(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace kb
+
+using namespace kb;
+
+extern "C" {
+
+long kb_conv_packed_floats(int Cout, int Cin, int ksize) {
+  if (Cout <= 0 || Cin <= 0 || ksize <= 0) return 0;
+  const long chunks = (Cin + kChunk - 1) / kChunk, cout_pad = (Cout + 15) / 16 * 16;
+  return (long)ksize * ksize * chunks * cout_pad * kChunk;
+}
+
+int kb_conv_pack_weights(const float *w_oihw, int Cout, int Cin, int ksize, const float *out_scale, float *packed,
+                         kb_stream_t stream) {
+  KB_REQUIRE(w_oihw && packed && Cout > 0 && Cin > 0 && ksize > 0, "kb_conv_pack_weights: bad arguments");
+  const int chunks = (Cin + kChunk - 1) / kChunk, cout_pad = (Cout + 15) / 16 * 16;
+  const long total = kb_conv_packed_floats(Cout, Cin, ksize);
+  k_pack_weights<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, ksize, chunks, cout_pad, out_scale,
+                                                                    packed, total);
+  count_launch();
+  return check_launch("kb_conv_pack_weights");
+}
+
+int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
+  KB_REQUIRE(a && a->x && a->w_packed, "kb_conv2d: null argument");
+  KB_REQUIRE(a->N > 0 && a->H > 0 && a->W > 0 && a->Cin > 0 && a->Cout > 0, "kb_conv2d: bad shape");
+  KB_REQUIRE(a->x_stride >= a->Cin && a->x_stride % 4 == 0, "kb_conv2d: x_stride must be a multiple of 4 floats and >= Cin");
+  KB_REQUIRE((reinterpret_cast<uintptr_t>(a->x) & 15) == 0, "kb_conv2d: x must be 16-byte aligned");
+  KB_REQUIRE(a->ksize >= 1 && a->ksize <= 7 && (a->stride == 1 || a->stride == 2) && a->pad >= 0, "kb_conv2d: unsupported filter");
+  KB_REQUIRE(a->n_out >= 1 && a->n_out <= kMaxOut, "kb_conv2d: need 1..3 outputs");
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) {
+    set_error("kb_conv2d: cuTensorMapEncodeTiled is not available from the driver");
+    return KB_ENOSUP;
+  }
+  ConvKernelParams p;
+  memset(&p, 0, sizeof(p));
+  p.Ho = (a->H + 2 * a->pad - a->ksize) / a->stride + 1;
+  p.Wo = (a->W + 2 * a->pad - a->ksize) / a->stride + 1;
+  KB_REQUIRE(p.Ho > 0 && p.Wo > 0, "kb_conv2d: empty output");
+  if (a->out_H > 0) {
+    KB_REQUIRE(a->out_H <= p.Ho, "kb_conv2d: out_H exceeds the convolution output");
+    p.Ho = a->out_H;
+  }
+  if (a->out_W > 0) {
+    KB_REQUIRE(a->out_W <= p.Wo, "kb_conv2d: out_W exceeds the convolution output");
+    p.Wo = a->out_W;
+  }
+  p.tile_w = a->tile_w > 0 ? a->tile_w : (p.Wo >= 32 ? 32 : pow2_at_least(p.Wo));
+  KB_REQUIRE(p.tile_w <= kTileM && (p.tile_w & (p.tile_w - 1)) == 0, "kb_conv2d: tile_w must be a power of two <= 128");
+  p.tile_h = kTileM / p.tile_w;
+  p.tiles_x = (p.Wo + p.tile_w - 1) / p.tile_w;
+  p.tiles_y = (p.Ho + p.tile_h - 1) / p.tile_h;
+  p.chunks = (a->Cin + kChunk - 1) / kChunk;
+  p.ksize = a->ksize;
+  p.stride = a->stride;
+  p.pad = a->pad;
+  p.Cout = a->Cout;
+  p.Cout4 = (a->Cout + 3) & ~3;
+  const int cout_pad = (a->Cout + 15) / 16 * 16;
+  const long tiles = (long)p.tiles_x * p.tiles_y * a->N;
+  int npad = a->n_block > 0 ? a->n_block : cout_pad;
+  if (a->n_block <= 0) {
+    if (npad > 256) npad = 256;
+    // few tiles (deep, low-resolution rows): split the output channels over more CTAs to fill the 148 SMs
+    while (npad > 64 && npad % 32 == 0 && tiles * ((cout_pad + npad - 1) / npad) < 148) npad /= 2;
+  }
+  KB_REQUIRE(npad % 16 == 0 && npad >= 16 && npad <= 256, "kb_conv2d: n_block must be a multiple of 16 in [16,256]");
+  p.Npad = npad;
+  const int n_blocks = (cout_pad + npad - 1) / npad;
+  p.tmem_cols = (uint32_t)max(32, pow2_at_least(npad));
+  const int stage_bytes = kABytes + npad * kChunk * 4;
+  const int J = a->ksize * a->ksize * p.chunks;
+  int stages = a->stages > 0 ? a->stages : (stage_bytes * 4 <= 100 * 1024 ? 4 : (200 * 1024) / stage_bytes);
+  stages = max(2, min(min(stages, 8), max(J, 2)));
+  p.stages = stages;
+  p.bias = a->bias;
+  p.res = a->res;
+  p.res_stride = a->res_stride;
+  if (a->res) KB_REQUIRE(a->res_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(a->res) & 15) == 0, "kb_conv2d: residual alignment");
+  p.n_out = a->n_out;
+  for (int o = 0; o < a->n_out; ++o) {
+    KB_REQUIRE(a->out[o].ptr && a->out[o].pixel_stride % 4 == 0 && a->out[o].pixel_stride >= p.Cout4 &&
+                   (reinterpret_cast<uintptr_t>(a->out[o].ptr) & 15) == 0,
+               "kb_conv2d: output %d: pointer / stride must be 16-byte aligned and hold %d channels", o, p.Cout4);
+    p.out[o].ptr = a->out[o].ptr;
+    p.out[o].stride = a->out[o].pixel_stride;
+    p.out[o].slope = a->out[o].slope;
+    p.out[o].round_tf32 = a->out[o].round_tf32;
+  }
+
+  // A: NHWC activations as a 4-D tensor {C, W, H, N}; box {32, tile_w*stride, tile_h*stride, 1} traversed with the
+  // convolution stride -> tile_w x tile_h pixels x 32 channels = 128 rows of 128 bytes, 128B-swizzled.
+  CUtensorMap map_a, map_b;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->N};
+    cuuint64_t strides[3] = {(cuuint64_t)a->x_stride * 4, (cuuint64_t)a->x_stride * 4 * a->W,
+                             (cuuint64_t)a->x_stride * 4 * a->W * a->H};
+    cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)(p.tile_w * a->stride), (cuuint32_t)(p.tile_h * a->stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)a->stride, (cuuint32_t)a->stride, 1};
+    CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(a->x), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("kb_conv2d: cuTensorMapEncodeTiled(activations) failed with CUresult %d", (int)r);
+      return KB_EINVAL;
+    }
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)kChunk, (cuuint64_t)cout_pad, (cuuint64_t)J};
+    cuuint64_t strides[2] = {(cuuint64_t)kChunk * 4, (cuuint64_t)kChunk * 4 * cout_pad};
+    cuuint32_t box[3] = {(cuuint32_t)kChunk, (cuuint32_t)npad, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(a->w_packed), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("kb_conv2d: cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r);
+      return KB_EINVAL;
+    }
+  }
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) {
+      set_error("kb_conv2d: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    smem_set = 227 * 1024;
+  }
+  KB_REQUIRE(smem <= 227 * 1024, "kb_conv2d: pipeline does not fit shared memory");
+  dim3 grid((unsigned)tiles, (unsigned)n_blocks);
+  k_conv_tf32<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  count_launch();
+  return check_launch("kb_conv2d");
+}
+
+int kb_upsample2x_prelu(const float *x, long x_stride, int N, int H, int W, int C, const float *slope, float *y, long y_stride,
+                        int Ho, int Wo, int round_tf32, kb_stream_t stream) {
+  KB_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0 && Ho <= 2 * H && Wo <= 2 * W,
+             "kb_upsample2x_prelu: bad arguments");
+  KB_REQUIRE(x_stride % 4 == 0 && y_stride % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0,
+             "kb_upsample2x_prelu: pointers must be 16-byte aligned, strides multiples of 4 floats");
+  const int C4 = (C + 3) / 4;
+  const long total = (long)N * Ho * Wo * C4;
+  k_upsample2x_prelu<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, x_stride, H, W, C4, slope, C, y, y_stride, Ho, Wo,
+                                                                        round_tf32, total);
+  count_launch();
+  return check_launch("kb_upsample2x_prelu");
+}
+
+int kb_prelu_nhwc(const float *x, long x_stride, long pixels, int C, const float *slope, float *y, long y_stride, int round_tf32,
+                  kb_stream_t stream) {
+  KB_REQUIRE(x && y && pixels > 0 && C > 0 && x_stride % 4 == 0 && y_stride % 4 == 0 &&
+                 ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0,
+             "kb_prelu_nhwc: bad arguments (16-byte aligned pointers, strides multiples of 4 floats)");
+  const int C4 = (C + 3) / 4;
+  const long total = pixels * C4;
+  k_prelu_nhwc<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, x_stride, slope, C, C4, y, y_stride, round_tf32, total);
+  count_launch();
+  return check_launch("kb_prelu_nhwc");
+}
+
+int kb_maxpool2_ceil(const float *x, long x_stride, int N, int H, int W, int C, float *y, long y_stride, kb_stream_t stream) {
+  KB_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && x_stride % 4 == 0 && y_stride % 4 == 0 &&
+                 ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0,
+             "kb_maxpool2_ceil: bad arguments (16-byte aligned pointers, strides multiples of 4 floats)");
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, C4 = (C + 3) / 4;
+  const long total = (long)N * Ho * Wo * C4;
+  k_maxpool2_ceil<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, x_stride, H, W, C4, y, y_stride, Ho, Wo, total);
+  count_launch();
+  return check_launch("kb_maxpool2_ceil");
+}
+
+int kb_nchw_to_nhwc(const float *x, int N, int C, int H, int W, float *y, long y_stride, float sub, float mul,
+                    kb_stream_t stream) {
+  KB_REQUIRE(x && y && N > 0 && C > 0 && H > 0 && W > 0 && y_stride % 4 == 0 && y_stride >= ((C + 3) & ~3),
+             "kb_nchw_to_nhwc: bad arguments");
+  KB_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0, "kb_nchw_to_nhwc: destination must be 16-byte aligned");
+  const int C4 = (C + 3) / 4;
+  const long HW = (long)H * W, total = (long)N * C4 * HW;
+  k_nchw_to_nhwc<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, C, HW, y, y_stride, C4, sub, mul, total);
+  count_launch();
+  return check_launch("kb_nchw_to_nhwc");
+}
+
+int kb_nhwc_to_nchw(const float *x, long x_stride, int N, int C, int H, int W, float *y, float mul, float add,
+                    kb_stream_t stream) {
+  KB_REQUIRE(x && y && N > 0 && C > 0 && H > 0 && W > 0, "kb_nhwc_to_nchw: bad arguments");
+  const long HW = (long)H * W, total = (long)N * C * HW;
+  k_nhwc_to_nchw<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, x_stride, C, HW, y, mul, add, total);
+  count_launch();
+  return check_launch("kb_nhwc_to_nchw");
+}
+
+}  // extern "C"

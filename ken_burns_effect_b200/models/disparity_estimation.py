@@ -4,18 +4,21 @@ import torch
 import torch.nn as nn
 import torchvision
 
+from ..utils import convstack as cs
 from .gridnet import Basic, add_grid, grid_forward, grid_name
 
 
 def _vgg19_bn_features():
     """torchvision's VGG19-bn feature stack.  The reference asks for ImageNet weights
-    (disparity_estimation.py:86); they are used when torchvision can find them in the local hub cache and
-    silently replaced by the default initialisation when it cannot (no network in this environment).
-    The weights are not part of any released .tar checkpoint."""
-    try:
-        return torchvision.models.vgg19_bn(weights=torchvision.models.VGG19_BN_Weights.IMAGENET1K_V1).features.eval()
-    except Exception:
-        return torchvision.models.vgg19_bn(weights=None).features.eval()
+    (disparity_estimation.py:86); they are loaded when the checkpoint file already sits in the local torch hub
+    cache and replaced by the default initialisation when it does not (no download is ever attempted: there is
+    no network in this environment).  The weights are not part of any released .tar checkpoint."""
+    import os
+    weights = torchvision.models.VGG19_BN_Weights.IMAGENET1K_V1
+    cached = os.path.join(torch.hub.get_dir(), 'checkpoints', os.path.basename(weights.url))
+    if os.path.exists(cached):
+        return torchvision.models.vgg19_bn(weights=weights).features.eval()
+    return torchvision.models.vgg19_bn(weights=None).features.eval()
 
 
 class Semantics(nn.Module):
@@ -35,7 +38,25 @@ class Semantics(nn.Module):
         x = tensorInput[:, [2, 1, 0], :, :]
         mean = x.new_tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
         std = x.new_tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
-        return self.moduleVgg((x - mean) / std)
+        x = (x - mean) / std
+        return self._vgg_b200(x) if x.is_cuda else self.moduleVgg(x)
+
+    def _vgg_b200(self, x):
+        """The VGG19-bn trunk on libkb200 convolutions: eval-mode BatchNorm folded into filter and bias, ReLU in the
+        epilogue (PReLU with slope 0), ceil-mode 2x2 max-pool as its own NHWC kernel."""
+        h = cs.to_nhwc(x)
+        for layer in self.moduleVgg:
+            if isinstance(layer, nn.MaxPool2d):
+                h = cs.maxpool2_ceil(h)
+                continue
+            conv, bn, _relu = list(layer)
+            zero = getattr(self, '_relu_slopes', {}).get(conv.out_channels)
+            if zero is None or zero.device != x.device:
+                if not hasattr(self, '_relu_slopes'):
+                    object.__setattr__(self, '_relu_slopes', {})
+                zero = self._relu_slopes[conv.out_channels] = torch.zeros(conv.out_channels, device=x.device)
+            h, = cs.conv2d(h, cs.packed(conv, bn), [(zero, True, None)])
+        return cs.to_nchw(h)
 
 
 class Disparity(nn.Module):
@@ -49,7 +70,16 @@ class Disparity(nn.Module):
         add_grid(self, self.FEATURES)
         self.moduleDisparity = Basic('conv-relu-conv', [32, 32, 1])
 
+    def _forward_b200(self, tensorImage, tensorSemantics):
+        x = cs.to_nhwc(tensorImage)
+        sem, = cs.conv2d(cs.to_nhwc(tensorSemantics), cs.packed(self.moduleSemantics), [(None, False, None)])
+        row0 = cs.grid_forward_nhwc(self, self.FEATURES, lambda outs: cs.conv2d(x, cs.packed(self.moduleImage), outs),
+                                    semantics_res=sem)
+        return cs.to_nchw(cs.head_nhwc(self.moduleDisparity, row0))
+
     def forward(self, tensorImage, tensorSemantics):
+        if tensorImage.is_cuda:
+            return self._forward_b200(tensorImage, tensorSemantics)
         m = self._modules
         rows = [self.moduleImage(tensorImage)]
         for r in range(1, len(self.FEATURES)):

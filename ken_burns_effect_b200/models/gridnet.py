@@ -131,6 +131,7 @@ def sample_norm(tensorImage, tensorDisparity):
     """Per-sample mean / unbiased std of image and disparity as [B,1,1,1] tensors
     (models/disparity_refinement.py:84-85, models/pointcloud_inpainting.py:219-220)."""
     B = tensorImage.size(0)
-    mean = [tensorImage.view(B, -1).mean(1, True).view(B, 1, 1, 1), tensorDisparity.view(B, -1).mean(1, True).view(B, 1, 1, 1)]
-    std = [tensorImage.view(B, -1).std(1, True).view(B, 1, 1, 1), tensorDisparity.view(B, -1).std(1, True).view(B, 1, 1, 1)]
+    img, disp = tensorImage.reshape(B, -1), tensorDisparity.reshape(B, -1)   # (.view in the reference: contiguous inputs there)
+    mean = [img.mean(1, True).view(B, 1, 1, 1), disp.mean(1, True).view(B, 1, 1, 1)]
+    std = [img.std(1, True).view(B, 1, 1, 1), disp.std(1, True).view(B, 1, 1, 1)]
     return mean, std

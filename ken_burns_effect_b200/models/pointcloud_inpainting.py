@@ -6,6 +6,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..utils import common as kb
+from ..utils import convstack as cs
 from .gridnet import Basic, add_grid, grid_forward, grid_name, sample_norm
 
 
@@ -53,16 +54,39 @@ class Inpaint(nn.Module):
         if tensorData is None and tensorContext is not None:
             tensorData = torch.cat([tensorImage, tensorDisparity, tensorContext], 1)
         elif tensorData is None:
-            tensorContext = self.moduleContext(torch.cat([tensorImage, tensorDisparity], 1))
+            tensorContext = (self._context_b200(tensorImage, tensorDisparity) if tensorImage.is_cuda
+                             else self.moduleContext(torch.cat([tensorImage, tensorDisparity], 1)))
             tensorData = torch.cat([tensorImage, tensorDisparity, tensorContext], 1)
 
-        rows = grid_forward(self, self._column0(tensorData, tensorMasks))
-        img, disp = self.normalize_images_disp(self.moduleImage(rows[0]), self.moduleDisparity(rows[0]), not_normed=False)
+        if tensorData.is_cuda:
+            img, disp = self._grid_b200(tensorData, tensorMasks)
+        else:
+            rows = grid_forward(self, self._column0(tensorData, tensorMasks))
+            img, disp = self.moduleImage(rows[0]), self.moduleDisparity(rows[0])
+        img, disp = self.normalize_images_disp(img, disp, not_normed=False)
         return {
             'tensorExisting': tensorMasks,
             'tensorImage': img.clamp(0.0, 1.0) if self.training == False else img,  # noqa: E712
             'tensorDisparity': F.threshold(input=disp, threshold=0.0, value=0.0),
         }
+
+    # -- the same forward on libkb200's tcgen05 convolutions (NHWC, fused epilogues; utils/convstack.py) ---------
+    def _grid_b200(self, tensorData, tensorMasks):
+        N, C, H, W = tensorData.shape
+        buf = torch.empty(N, H, W, cs.round4(C + 1), device=tensorData.device, dtype=torch.float32)
+        cs.to_nhwc(tensorData, dst=buf[..., :C])                       # torch.cat([tensorData, tensorMasks], 1), :135
+        cs.to_nhwc(tensorMasks, dst=buf[..., C:C + 1])
+        x = buf[..., :C + 1]
+        row0 = cs.grid_forward_nhwc(self, self.FEATURES, lambda outs: cs.run_block(self.moduleInput, x, outs, x_raw=x))
+        return cs.to_nchw(cs.head_nhwc(self.moduleImage, row0)), cs.to_nchw(cs.head_nhwc(self.moduleDisparity, row0))
+
+    def _context_b200(self, img, disp):
+        """moduleContext (:89-94): conv(4->64) PReLU conv(64->64) PReLU, returned NCHW for the 68-channel splat."""
+        x = cs.to_nhwc(torch.cat([img, disp], 1))
+        c0, a0, c1, a1 = list(self.moduleContext)
+        t, = cs.conv2d(x, cs.packed(c0), [(a0.weight, True, None)])
+        y, = cs.conv2d(t, cs.packed(c1), [(a1.weight, False, None)])
+        return cs.to_nchw(y)
 
     # -- models/pointcloud_inpainting.py:185-213 ------------------------------------------------------
     def _render_inputs(self, tensorImage, tensorDisparity, tensorShift, objectCommon, dblFocal):
@@ -73,7 +97,7 @@ class Inpaint(nn.Module):
         valid = (kb.spatial_filter(tensorDisparity / tensorDisparity.max(), 'laplacian').abs() < 0.03).float()
         points = kb.depth_to_points(depth * valid, dblFocal).view(1, 3, -1)
         img, disp = self.normalize_images_disp(tensorImage, tensorDisparity, not_normed=True)
-        context = self.moduleContext(torch.cat([img, disp], 1))
+        context = self._context_b200(img, disp) if img.is_cuda else self.moduleContext(torch.cat([img, disp], 1))
         render, existing = kb.render_pointcloud(points + tensorShift, torch.cat([img, disp, context], 1).view(1, 68, -1),
                                                 objectCommon['intWidth'], objectCommon['intHeight'], dblFocal,
                                                 objectCommon['dblBaseline'])

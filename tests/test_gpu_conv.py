@@ -1,0 +1,146 @@
+"""GPU parity tests of the tcgen05 convolution path (kb_conv2d & companions, utils/convstack.py).
+
+Ground truth:
+  * single ops: torch fp32 on the GPU with TF32 disabled (plain fp32 reference of the same op);
+  * whole networks: outputs of the REFERENCE's own modules (tests/golden/ref_torch_cpu.npz, fp32 CPU).
+The kernels multiply in TF32 (10-bit mantissa operands, fp32 accumulation) -- what cuDNN does for the reference under
+PyTorch's default allow_tf32 -- so the bar is a relative L2 error, stated per test: 2e-3 for one convolution,
+1e-2 for a whole network (~60 convolutions deep).  north_star's 1e-3 bar is on the rendered RGB/depth, tested
+in test_gpu_pipeline.py.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import kb_helpers
+from ken_burns_effect_b200.utils import convstack as cs
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_torch_cpu.npz"))
+torch.set_grad_enabled(False)
+
+
+@pytest.fixture(autouse=True)
+def _fp32_reference():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def rel(a, b):
+    return kb_helpers.rel_l2(a.detach().float().cpu().numpy(), b.detach().float().cpu().numpy())
+
+
+def nhwc(x):
+    return cs.to_nhwc(x)
+
+
+# (Cin, Cout, k, stride, pad, H, W)
+CONV_CASES = [
+    (32, 32, 3, 1, 1, 64, 96),      # the full-resolution GridNet row
+    (32, 32, 3, 1, 1, 37, 53),      # ragged: tiles hang over both borders
+    (4, 64, 3, 1, 1, 40, 52),       # context extractor, 4 input channels (TMA zero-fills channels 4..31)
+    (69, 32, 3, 1, 1, 33, 47),      # moduleInput: 69 channels in a 72-float pixel
+    (69, 32, 1, 1, 0, 33, 47),      # its 1x1 shortcut
+    (64, 128, 3, 2, 1, 48, 64),     # Downsample's stride-2 conv
+    (32, 64, 3, 2, 1, 45, 61),      # stride 2, odd size
+    (3, 32, 7, 2, 3, 50, 70),       # Disparity stem
+    (256, 256, 3, 1, 1, 24, 32),
+    (512, 512, 3, 1, 1, 12, 16),    # two output-channel blocks
+    (32, 3, 3, 1, 1, 40, 40),       # colour head
+    (24, 1, 3, 1, 1, 40, 40),       # disparity head
+    (144, 48, 3, 1, 1, 30, 44),     # Refine decoder
+    (1, 96, 3, 1, 1, 20, 28),
+]
+
+
+@pytest.mark.parametrize("Cin,Cout,k,stride,pad,H,W", CONV_CASES)
+def test_conv2d_vs_torch_fp32(Cin, Cout, k, stride, pad, H, W):
+    g = torch.Generator().manual_seed(Cin * 1000 + Cout * 7 + k)
+    conv = torch.nn.Conv2d(Cin, Cout, k, stride, pad).cuda()
+    conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * (2.0 / (Cin * k * k)) ** 0.5)
+    conv.bias.copy_(torch.randn(Cout, generator=g) * 0.1)
+    x = torch.randn(2, Cin, H, W, generator=g).cuda()
+    slope = (0.25 + 0.1 * torch.randn(Cout, generator=g)).cuda()
+    ref = conv(x)
+    res = torch.randn(ref.shape, generator=g).cuda()
+    outs = cs.conv2d(nhwc(x), cs.packed(conv), [(None, False, None), (slope, False, None), (slope, True, None)], res=nhwc(res))
+    torch.cuda.synchronize()
+    want = ref + res
+    assert outs[0].shape == (2, want.shape[2], want.shape[3], Cout)
+    assert rel(outs[0].permute(0, 3, 1, 2), want) < 2e-3
+    assert rel(outs[1].permute(0, 3, 1, 2), F.prelu(want, slope)) < 2e-3
+    assert rel(outs[2].permute(0, 3, 1, 2), F.prelu(want, slope)) < 2e-3
+    # allocation padding channels must be exact zeros (they are read as K padding by the next convolution)
+    full = outs[0].as_strided((2, outs[0].size(1), outs[0].size(2), cs.round4(Cout)), outs[0].stride())
+    assert float(full[..., Cout:].abs().sum()) == 0.0
+
+
+def test_conv2d_exact_on_tf32_representable_inputs():
+    """With inputs and weights that are exactly representable in TF32 and small integers, the tensor-core result
+    must equal the fp32 convolution bit for bit: catches any layout / swizzle / descriptor mistake that a
+    tolerance would blur."""
+    g = torch.Generator().manual_seed(5)
+    conv = torch.nn.Conv2d(64, 48, 3, 1, 1).cuda()
+    conv.weight.copy_(torch.randint(-3, 4, conv.weight.shape, generator=g).float())
+    conv.bias.copy_(torch.randint(-3, 4, (48,), generator=g).float())
+    x = torch.randint(-4, 5, (1, 64, 29, 41), generator=g).float().cuda()
+    out, = cs.conv2d(nhwc(x), cs.packed(conv), [(None, False, None)])
+    # exact reference in float64 on the CPU (cuDNN's fp32 algorithms -- FFT / Winograd -- are not exact on integers)
+    want = F.conv2d(x.double().cpu(), conv.weight.double().cpu(), conv.bias.double().cpu(), 1, 1)
+    assert torch.equal(out.permute(0, 3, 1, 2).double().cpu(), want)
+
+
+def test_conv2d_into_concat_slice_and_crop():
+    g = torch.Generator().manual_seed(9)
+    conv = torch.nn.Conv2d(32, 24, 3, 1, 1).cuda()
+    x = torch.randn(1, 32, 31, 45, generator=g).cuda()
+    buf = torch.full((1, 30, 44, 72), 7.0, device="cuda")
+    cs.conv2d(nhwc(x), cs.packed(conv), [(None, False, buf[..., 24:48])], crop=(30, 44))
+    ref = conv(x)[:, :, :30, :44]
+    assert rel(buf[..., 24:48].permute(0, 3, 1, 2), ref) < 2e-3
+    assert float((buf[..., :24] - 7.0).abs().max()) == 0.0 and float((buf[..., 48:] - 7.0).abs().max()) == 0.0
+
+
+def test_elementwise_companions():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 20, 13, 17, generator=g).cuda()
+    slope = (0.25 + 0.1 * torch.randn(20, generator=g)).cuda()
+    up = F.prelu(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False), slope)
+    got = cs.upsample2x_prelu(nhwc(x), slope, rnd=False)
+    assert rel(got.permute(0, 3, 1, 2), up) < 1e-6
+    got = cs.upsample2x_prelu(nhwc(x), slope, out_hw=(25, 33), rnd=False)
+    assert rel(got.permute(0, 3, 1, 2), up[:, :, :25, :33]) < 1e-6
+    assert torch.equal(cs.maxpool2_ceil(nhwc(x)).permute(0, 3, 1, 2), F.max_pool2d(x, 2, 2, ceil_mode=True))
+    assert torch.equal(cs.prelu(nhwc(x), slope, rnd=False).permute(0, 3, 1, 2), F.prelu(x, slope))
+    assert torch.equal(cs.to_nchw(nhwc(x)), x)
+    assert torch.allclose(cs.to_nchw(cs.to_nhwc(x, sub=0.5, mul=2.0), mul=0.5, add=0.5), x, atol=1e-6)
+
+
+def T(k):
+    return torch.from_numpy(G[k]).cuda()
+
+
+def test_networks_vs_reference_goldens():
+    from ken_burns_effect_b200.models.disparity_estimation import Disparity, Semantics
+    from ken_burns_effect_b200.models.disparity_refinement import Refine
+    from ken_burns_effect_b200.models.disparity_refinement_pretrained import Refine as RefineP
+    from ken_burns_effect_b200.models.pointcloud_inpainting import Inpaint
+    sem = kb_helpers.deterministic_state(Semantics().eval()).cuda()
+    dis = kb_helpers.deterministic_state(Disparity().eval()).cuda()
+    s = sem(T("net_img"))
+    assert rel(s, T("net_semantics")) < 1e-2
+    assert rel(dis(T("net_img"), T("net_semantics")), T("net_disparity")) < 1e-2
+    assert rel(kb_helpers.deterministic_state(Refine().eval()).cuda()(T("ref_img"), T("ref_disp_lo")), T("ref_refine")) < 1e-2
+    assert rel(kb_helpers.deterministic_state(RefineP().eval()).cuda()(T("ref_img"), T("ref_disp_lo")),
+               T("ref_refine_pretrained")) < 1e-2
+    net = kb_helpers.deterministic_state(Inpaint().eval()).cuda()
+    mask = T("inp_mask")
+    o = net(mask, tensorImage=T("ref_img") * mask, tensorDisparity=T("inp_disp") * mask)
+    for k in ("tensorExisting", "tensorImage", "tensorDisparity"):
+        assert rel(o[k], T(f"inpaint_{k}")) < 1e-2, k

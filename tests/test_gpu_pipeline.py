@@ -74,7 +74,9 @@ def test_pointcloud_inpainting_render_inputs_vs_oracle():
         valid = (kb.spatial_filter(td / td.max(), 'laplacian').abs() < 0.03).float()
         pts = (kb.depth_to_points(depth * valid, focal).view(1, 3, -1) + shift).cpu().numpy()
         im, dn = net.normalize_images_disp(ti, td, not_normed=True)
-        ctx = net.moduleContext(torch.cat([im, dn], 1))
+        ctx = net._context_b200(im, dn)      # the product's own context features (tcgen05 TF32 convs) ...
+        ctx_fp32 = net.moduleContext(torch.cat([im, dn], 1))   # ... which must agree with the fp32 cuDNN ones
+        assert kb_helpers.rel_l2(ctx.cpu().numpy(), ctx_fp32.cpu().numpy()) < 2e-3
         data = torch.cat([im, dn, ctx], 1).view(1, 68, -1).cpu().numpy()
     oracle.set_threads(0)
     o_render, o_exist = oracle.render_pointcloud(pts, data, W, H, focal, 120)
