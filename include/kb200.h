@@ -156,6 +156,7 @@ typedef struct kb_conv_args {
   int tile_w;            /* 0 = auto; output tile is tile_w x (128/tile_w) pixels */
   int n_block;           /* 0 = auto; output channels per CTA (multiple of 16, <= 256) */
   int stages;            /* 0 = auto; shared-memory pipeline depth */
+  int algo;              /* 0 = auto; 1 = one TMA load per filter tap (any filter); 2 = persistent halo kernel (stride 1, k <= 3) */
 } kb_conv_args;
 
 /* out_o = prelu_o(conv(x, w) + bias + res)   for o < n_out;  one launch. */

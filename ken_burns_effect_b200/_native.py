@@ -35,7 +35,7 @@ class KBConvArgs(ctypes.Structure):
     _fields_ = [("x", c_void), ("N", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("x_stride", c_long),
                 ("w_packed", c_void), ("bias", c_void), ("Cout", c_int), ("ksize", c_int), ("stride", c_int),
                 ("pad", c_int), ("res", c_void), ("res_stride", c_long), ("n_out", c_int), ("out", KBConvOut * 3),
-                ("out_H", c_int), ("out_W", c_int), ("tile_w", c_int), ("n_block", c_int), ("stages", c_int)]
+                ("out_H", c_int), ("out_W", c_int), ("tile_w", c_int), ("n_block", c_int), ("stages", c_int), ("algo", c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol include/kb200.h declares (tests/test_abi.py checks).

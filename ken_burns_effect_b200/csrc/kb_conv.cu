@@ -21,6 +21,7 @@
 //   * a ring of `stages` shared-memory slots with full/empty mbarriers decouples TMA from the tensor pipe;
 //     small-N layers fit two CTAs per SM so one CTA's epilogue overlaps the other's main loop.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -125,7 +126,7 @@ __device__ __forceinline__ float round_tf32(float v) {
 constexpr int kTileM = 128;            // output pixels per CTA = UMMA M
 constexpr int kChunk = 32;             // input channels per K step (32 fp32 = one 128-byte swizzle row)
 constexpr int kABytes = kTileM * kChunk * 4;
-constexpr int kConvThreads = 192;      // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kConvThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int kMaxOut = 3;
 
 struct ConvOut {
@@ -147,8 +148,79 @@ struct ConvKernelParams {
   const float *res;
   long res_stride;
   int n_out;
+  int vec;              // bias / slope arrays can be read as float4 (Cout % 4 == 0, 16-byte aligned)
   ConvOut out[kMaxOut];
+  // persistent halo kernel only
+  int pitch;            // halo row pitch in pixels (>= tile_w + ksize - 1)
+  int a_stage_bytes;    // one halo slice (32 channels), rounded up to 1024
+  int a_stages, b_stages;
+  int resident;         // all weight panels stay in shared memory for the life of the CTA
+  int n_blocks;
+  long work_items;      // tiles * n_blocks
+  int debug;            // KB_CONV_DEBUG (profiling experiments only): 1 = no epilogue stores, 2 = no MMAs
 };
+
+
+// Epilogue of one accumulator row (= one output pixel): TMEM -> registers, + bias, + residual, then every requested
+// output (own PReLU, optional TF32 rounding) as 16-byte stores.  Warp-collective (tcgen05.ld).  Eight epilogue warps
+// share a tile: warp e reads TMEM lanes 32*(e%4).. and the 16-column chunks of parity e/4.
+// Channels Cout..round_up(Cout,4) come out as exact zeros without masking: their filter rows and bias are zero padding
+// and the residual's own padding channels are zero by the same rule.
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+__device__ __forceinline__ float4 ld_tail(const float *p, int c, int C) {   // p[c..c+3] with zeros beyond C
+  float4 r;
+  r.x = c < C ? __ldg(p + c) : 0.f;
+  r.y = c + 1 < C ? __ldg(p + c + 1) : 0.f;
+  r.z = c + 2 < C ? __ldg(p + c + 2) : 0.f;
+  r.w = c + 3 < C ? __ldg(p + c + 3) : 0.f;
+  return r;
+}
+
+__device__ __forceinline__ float prelu1(float v, float s) { return fmaxf(v, 0.f) + s * fminf(v, 0.f); }
+
+__device__ __forceinline__ void epilogue_rows(const ConvKernelParams &p, uint32_t taddr, int img, int oy, int ox, int n0, int half) {
+  const bool inside = (oy < p.Ho) & (ox < p.Wo);
+  const long pix = inside ? ((long)img * p.Ho + oy) * p.Wo + ox : 0;
+  const float *res = p.res ? p.res + pix * p.res_stride : nullptr;
+  float *dst[kMaxOut];
+#pragma unroll
+  for (int o = 0; o < kMaxOut; ++o) dst[o] = o < p.n_out ? p.out[o].ptr + pix * p.out[o].stride : nullptr;
+  const bool vec = p.vec != 0;
+  for (int c0 = 16 * half; c0 < p.Npad; c0 += 32) {
+    if (n0 + c0 >= p.Cout4) break;           // warp-uniform
+    float v[16];
+    tmem_ld16(taddr + (uint32_t)c0, v);
+    if (!inside) continue;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int c = n0 + c0 + 4 * g;
+      if (c >= p.Cout4) break;
+      float4 a = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+      if (p.bias) {
+        const float4 b = vec ? ldg4(p.bias + c) : ld_tail(p.bias, c, p.Cout);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      if (res) {
+        const float4 rr = *reinterpret_cast<const float4 *>(res + c);
+        a.x += rr.x; a.y += rr.y; a.z += rr.z; a.w += rr.w;
+      }
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) {
+        if (o >= p.n_out) break;
+        float4 w = a;
+        if (p.out[o].slope) {
+          const float4 sl = vec ? ldg4(p.out[o].slope + c) : ld_tail(p.out[o].slope, c, p.Cout);
+          w.x = prelu1(w.x, sl.x); w.y = prelu1(w.y, sl.y); w.z = prelu1(w.z, sl.z); w.w = prelu1(w.w, sl.w);
+        }
+        if (p.out[o].round_tf32) {
+          w.x = round_tf32(w.x); w.y = round_tf32(w.y); w.z = round_tf32(w.z); w.w = round_tf32(w.w);
+        }
+        if (!(p.debug & 1)) *reinterpret_cast<float4 *>(dst[o] + c) = w;
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kConvThreads) k_conv_tf32(const __grid_constant__ CUtensorMap map_a,
                                                             const __grid_constant__ CUtensorMap map_b,
@@ -194,97 +266,216 @@ __global__ void __launch_bounds__(kConvThreads) k_conv_tf32(const __grid_constan
   const int taps = p.ksize * p.ksize;
   const int J = taps * p.chunks;
 
+  // The single-thread issue loops below run on the uniform datapath, where every dependent instruction costs ~10
+  // cycles: ring indices are counters with explicit wrap-around (no division / modulo per step) and descriptors are
+  // a constant template plus a 14-bit address field.
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      for (int j = 0; j < J; ++j) {
-        const int s = j % p.stages;
-        const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
-        mbar_wait(empty + s, ph ^ 1u);
-        uint8_t *a_dst = smem + (size_t)s * stage_bytes;
-        uint8_t *b_dst = a_dst + kABytes;
-        const int tap = j / p.chunks, ck = j - tap * p.chunks;
-        const int r = tap / p.ksize, q = tap - r * p.ksize;
-        mbar_expect_tx(full + s, (uint32_t)stage_bytes);
-        tma_load_4d(&map_a, full + s, a_dst, ck * kChunk, x0 * p.stride + q - p.pad, y0 * p.stride + r - p.pad, img);
-        tma_load_3d(&map_b, full + s, b_dst, 0, n0, j);
-      }
+      uint32_t s = 0, ph = 0;
+      int j = 0;
+      const int cx = x0 * p.stride - p.pad, cy = y0 * p.stride - p.pad;
+      for (int r = 0; r < p.ksize; ++r)
+        for (int q = 0; q < p.ksize; ++q)
+          for (int ck = 0; ck < p.chunks; ++ck, ++j) {
+            mbar_wait(empty + s, ph ^ 1u);
+            uint8_t *a_dst = smem + (size_t)s * stage_bytes;
+            mbar_expect_tx(full + s, (uint32_t)stage_bytes);
+            tma_load_4d(&map_a, full + s, a_dst, ck * kChunk, cx + q, cy + r, img);
+            tma_load_3d(&map_b, full + s, a_dst + kABytes, 0, n0, j);
+            if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+          }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
       const uint32_t idesc = (1u << 4) /* D fp32 */ | (2u << 7) /* A tf32 */ | (2u << 10) /* B tf32 */ |
                              ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint64_t tmpl = umma_desc_sw128(0);
+      const uint32_t base_lo = smem_u32(smem) >> 4, stage_lo = (uint32_t)stage_bytes >> 4;
+      uint32_t s = 0, ph = 0, lo = base_lo;
       for (int j = 0; j < J; ++j) {
-        const int s = j % p.stages;
-        const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
         mbar_wait(full + s, ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t b_addr = a_addr + kABytes;
-        const uint64_t da = umma_desc_sw128(a_addr), db = umma_desc_sw128(b_addr);
+        const uint64_t da = tmpl | lo, db = tmpl | (lo + (kABytes >> 4));
 #pragma unroll
         for (int k = 0; k < kChunk / 8; ++k)   // UMMA K = 8 tf32 = 32 bytes: advance the start address inside the swizzle row
           umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (j | k) != 0);
         umma_commit(empty + s);                // slot reusable once these MMAs have read it
+        lo += stage_lo;
+        if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; lo = base_lo; }
       }
       umma_commit(acc_full);                   // accumulator complete
     }
   } else {
-    // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
-    const int q = warp & 3;
+    // ===== epilogue: warps 2..9; warp w may only touch TMEM lanes 32*(w%4) .. +31 =====
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const int m = q * 32 + lane;               // accumulator row = pixel of the tile
     const int py = m / p.tile_w, px = m - py * p.tile_w;
-    const int oy = y0 + py, ox = x0 + px;
-    const bool inside = (oy < p.Ho) & (ox < p.Wo);
-    const long pix = ((long)img * p.Ho + oy) * p.Wo + ox;
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c0 = 0; c0 < p.Npad; c0 += 16) {
-      if (n0 + c0 >= p.Cout4) break;           // warp-uniform
-      float v[16];
-      tmem_ld16(taddr + (uint32_t)c0, v);
-      if (!inside) continue;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int c = n0 + c0 + 4 * g;
-        if (c >= p.Cout4) break;
-        float4 a = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-        float bb[4] = {0.f, 0.f, 0.f, 0.f};
-        if (p.bias) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (c + e < p.Cout) bb[e] = __ldg(p.bias + c + e);
-        }
-        a.x += bb[0]; a.y += bb[1]; a.z += bb[2]; a.w += bb[3];
-        if (p.res) {
-          const float4 rr = *reinterpret_cast<const float4 *>(p.res + pix * p.res_stride + c);
-          a.x += rr.x; a.y += rr.y; a.z += rr.z; a.w += rr.w;
-        }
-        if (c + 1 >= p.Cout) a.y = 0.f;       // keep the padding channels of the allocation at zero
-        if (c + 2 >= p.Cout) a.z = 0.f;
-        if (c + 3 >= p.Cout) a.w = 0.f;
-#pragma unroll
-        for (int o = 0; o < kMaxOut; ++o) {
-          if (o >= p.n_out) break;
-          float4 w = a;
-          if (p.out[o].slope) {
-            float sl[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (c + e < p.Cout) sl[e] = __ldg(p.out[o].slope + c + e);
-            w.x = w.x > 0.f ? w.x : w.x * sl[0];
-            w.y = w.y > 0.f ? w.y : w.y * sl[1];
-            w.z = w.z > 0.f ? w.z : w.z * sl[2];
-            w.w = w.w > 0.f ? w.w : w.w * sl[3];
+    epilogue_rows(p, tmem_base + ((uint32_t)(q * 32) << 16), img, y0 + py, x0 + px, n0, half);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+
+// ---- persistent kernel for stride-1 filters: one halo load per tile instead of one load per tap -----------------------
+// The A operand of tap (r,s) is the SAME shared-memory halo tile {32 ch, pitch, tile_h+k-1} read through a descriptor whose
+// start address is moved by (r*pitch + s) pixels (128 bytes each): 8 consecutive output pixels of one image row are 8
+// consecutive 128-byte rows of the swizzle atom, and consecutive image rows are `pitch` pixels apart (the descriptor's
+// stride byte offset).  This cuts the L2 -> shared-memory traffic of a 3x3 filter from 9 tiles to ~1.4 tiles per output
+// tile.  CTAs are persistent: the TMA producer runs ahead across tiles, the accumulator is double-buffered in TMEM so the
+// epilogue of tile i overlaps the MMAs of tile i+1, and filters small enough stay resident in shared memory.
+constexpr int kHaloTileW = 8, kHaloTileH = 16;
+
+// Measured on B200 (tools/probe_halo.py, profiles/probe_halo_r01.jsonl): the tensor core applies the 128-byte swizzle XOR
+// to the ABSOLUTE shared-memory address bits [7,10), exactly like TMA does when it writes the tile.  A descriptor may
+// therefore start at any 128-byte row of a TMA-written tile and use any multiple of 128 bytes as its stride between
+// 8-row groups; the "matrix base offset" field must stay 0 (setting it to (addr >> 7) & 7 corrupts the result).
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int KS>
+__global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid_constant__ CUtensorMap map_a,
+                                                                    const __grid_constant__ CUtensorMap map_b,
+                                                                    const ConvKernelParams p) {
+  constexpr int kTaps = KS * KS;
+  constexpr int kPitch = kHaloTileW + KS - 1;                         // halo row pitch in pixels
+  constexpr int kBoxBytes = kPitch * (kHaloTileH + KS - 1) * kChunk * 4;   // expect-tx of one halo slice
+  constexpr int kAStage = (kBoxBytes + 1023) & ~1023;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_bytes = p.Npad * kChunk * 4;
+  uint8_t *smem_a = smem;
+  uint8_t *smem_b = smem + (size_t)p.a_stages * kAStage;
+  uint64_t *a_full = reinterpret_cast<uint64_t *>(smem_b + (size_t)p.b_stages * b_bytes);
+  uint64_t *a_empty = a_full + p.a_stages;
+  uint64_t *b_full = a_empty + p.a_stages;
+  uint64_t *b_empty = b_full + p.b_stages;
+  uint64_t *acc_full = b_empty + p.b_stages;
+  uint64_t *acc_empty = acc_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 8); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
+      bool first = true;
+      for (long w = blockIdx.x; w < p.work_items; w += gridDim.x) {
+        const int nb = (int)(w % p.n_blocks);
+        long t = w / p.n_blocks;
+        const int tx = (int)(t % p.tiles_x);
+        t /= p.tiles_x;
+        const int ty = (int)(t % p.tiles_y);
+        const int img = (int)(t / p.tiles_y);
+        const int cx = tx * kHaloTileW - p.pad, cy = ty * kHaloTileH - p.pad, cn = nb * p.Npad;
+        for (int ck = 0; ck < p.chunks; ++ck) {
+          mbar_wait(a_empty + sa, pha ^ 1u);
+          mbar_expect_tx(a_full + sa, (uint32_t)kBoxBytes);
+          tma_load_4d(&map_a, a_full + sa, smem_a + (size_t)sa * kAStage, ck * kChunk, cx, cy, img);
+          if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; }
+          if (!p.resident || first) {
+            int j = ck;                                   // packed weights: panel (tap, ck) at index tap*chunks + ck
+            for (int tap = 0; tap < kTaps; ++tap, j += p.chunks) {
+              mbar_wait(b_empty + sb, phb ^ 1u);
+              mbar_expect_tx(b_full + sb, (uint32_t)b_bytes);
+              tma_load_3d(&map_b, b_full + sb, smem_b + (size_t)sb * b_bytes, 0, cn, j);
+              if (++sb == (uint32_t)p.b_stages) { sb = 0; phb ^= 1u; }
+            }
           }
-          if (p.out[o].round_tf32) {
-            w.x = round_tf32(w.x); w.y = round_tf32(w.y); w.z = round_tf32(w.z); w.w = round_tf32(w.w);
-          }
-          *reinterpret_cast<float4 *>(p.out[o].ptr + pix * p.out[o].stride + c) = w;
         }
+        first = false;
       }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint64_t tmpl_a = umma_desc_sw128_sbo(0, kPitch * kChunk * 4), tmpl_b = umma_desc_sw128(0);
+      const uint32_t a_base_lo = smem_u32(smem_a) >> 4, b_base_lo = smem_u32(smem_b) >> 4, b_step_lo = (uint32_t)b_bytes >> 4;
+      uint32_t sa = 0, pha = 0, a_lo = a_base_lo;
+      uint32_t sb = 0, phb = 0, b_lo = b_base_lo;
+      uint32_t as = 0, phacc = 0;
+      bool first = true;
+      for (long w = blockIdx.x; w < p.work_items; w += gridDim.x) {
+        mbar_wait(acc_empty + as, phacc ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * (uint32_t)p.Npad;
+        if (p.resident) { sb = 0; b_lo = b_base_lo; }     // resident panels: slot index = ck*taps + tap, loaded once
+        for (int ck = 0; ck < p.chunks; ++ck) {
+          mbar_wait(a_full + sa, pha);
+          tc_fence_after();
+#pragma unroll
+          for (int tap = 0; tap < kTaps; ++tap) {
+            if (!p.resident || first) {
+              mbar_wait(b_full + sb, phb);
+              tc_fence_after();
+            }
+            const uint32_t a_off = (uint32_t)(((tap / KS) * kPitch + (tap % KS)) * kChunk * 4) >> 4;   // compile-time
+            if (!(p.debug & 2)) {
+#pragma unroll
+              for (int k = 0; k < kChunk / 8; ++k)
+                umma_tf32(d_tmem, tmpl_a | (uint64_t)(a_lo + a_off + 2 * k), tmpl_b | (uint64_t)(b_lo + 2 * k), idesc,
+                          (uint32_t)((ck != 0) | (tap != 0) | (k != 0)));
+            }
+            if (!p.resident) umma_commit(b_empty + sb);
+            b_lo += b_step_lo;
+            if (++sb == (uint32_t)p.b_stages) { sb = 0; phb ^= (p.resident ? 0u : 1u); b_lo = b_base_lo; }
+          }
+          umma_commit(a_empty + sa);
+          a_lo += kAStage >> 4;
+          if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; a_lo = a_base_lo; }
+        }
+        umma_commit(acc_full + as);
+        as ^= 1u;
+        if (as == 0) phacc ^= 1u;
+        first = false;
+      }
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int m = q * 32 + lane;
+    const int py = m / kHaloTileW, px = m - py * kHaloTileW;
+    uint32_t as = 0, phacc = 0;
+    for (long w = blockIdx.x; w < p.work_items; w += gridDim.x) {
+      const int nb = (int)(w % p.n_blocks);
+      long t = w / p.n_blocks;
+      const int tx = (int)(t % p.tiles_x);
+      t /= p.tiles_x;
+      const int ty = (int)(t % p.tiles_y);
+      const int img = (int)(t / p.tiles_y);
+      mbar_wait(acc_full + as, phacc);
+      tc_fence_after();
+      epilogue_rows(p, tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.Npad, img, ty * kHaloTileH + py,
+                    tx * kHaloTileW + px, nb * p.Npad, half);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
+      as ^= 1u;
+      if (as == 0) phacc ^= 1u;
     }
   }
   tc_fence_before();
@@ -474,6 +665,67 @@ int kb_conv_pack_weights(const float *w_oihw, int Cout, int Cin, int ksize, cons
   return check_launch("kb_conv_pack_weights");
 }
 
+static int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+static int make_weight_map(EncodeTiledFn enc, const float *w_packed, int cout_pad, int J, int npad, CUtensorMap *map) {
+  cuuint64_t dims[3] = {(cuuint64_t)kChunk, (cuuint64_t)cout_pad, (cuuint64_t)J};
+  cuuint64_t strides[2] = {(cuuint64_t)kChunk * 4, (cuuint64_t)kChunk * 4 * cout_pad};
+  cuuint32_t box[3] = {(cuuint32_t)kChunk, (cuuint32_t)npad, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(w_packed), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("kb_conv2d: cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r);
+    return KB_EINVAL;
+  }
+  return 0;
+}
+
+// NHWC activations as a 4-D tensor {C, W, H, N}; box {32, box_w, box_h, 1} traversed with the convolution stride.
+static int make_act_map(EncodeTiledFn enc, const kb_conv_args *a, int box_w, int box_h, int stride, CUtensorMap *map) {
+  cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->N};
+  cuuint64_t strides[3] = {(cuuint64_t)a->x_stride * 4, (cuuint64_t)a->x_stride * 4 * a->W,
+                           (cuuint64_t)a->x_stride * 4 * a->W * a->H};
+  cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(a->x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("kb_conv2d: cuTensorMapEncodeTiled(activations) failed with CUresult %d", (int)r);
+    return KB_EINVAL;
+  }
+  return 0;
+}
+
+static int raise_smem_limit() {
+  static bool done = false;
+  if (done) return 0;
+  cudaError_t e = cudaFuncSetAttribute(k_conv_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  if (e != cudaSuccess) {
+    set_error("kb_conv2d: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  done = true;
+  return 0;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
   KB_REQUIRE(a && a->x && a->w_packed, "kb_conv2d: null argument");
   KB_REQUIRE(a->N > 0 && a->H > 0 && a->W > 0 && a->Cin > 0 && a->Cout > 0, "kb_conv2d: bad shape");
@@ -499,11 +751,12 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
     KB_REQUIRE(a->out_W <= p.Wo, "kb_conv2d: out_W exceeds the convolution output");
     p.Wo = a->out_W;
   }
-  p.tile_w = a->tile_w > 0 ? a->tile_w : (p.Wo >= 32 ? 32 : pow2_at_least(p.Wo));
-  KB_REQUIRE(p.tile_w <= kTileM && (p.tile_w & (p.tile_w - 1)) == 0, "kb_conv2d: tile_w must be a power of two <= 128");
-  p.tile_h = kTileM / p.tile_w;
-  p.tiles_x = (p.Wo + p.tile_w - 1) / p.tile_w;
-  p.tiles_y = (p.Ho + p.tile_h - 1) / p.tile_h;
+  // algo: 1 = one TMA load per filter tap (any filter), 2 = persistent halo kernel (stride 1, k <= 3)
+  const bool halo_ok = a->stride == 1 && (a->ksize == 1 || a->ksize == 3) && a->pad == a->ksize / 2;
+  int algo = a->algo > 0 ? a->algo : env_int("KB_CONV_ALGO", 0);
+  if (algo == 0) algo = halo_ok ? 2 : 1;
+  KB_REQUIRE(algo == 1 || (algo == 2 && halo_ok), "kb_conv2d: algo 2 needs stride 1, ksize <= 3, 'same' padding");
+
   p.chunks = (a->Cin + kChunk - 1) / kChunk;
   p.ksize = a->ksize;
   p.stride = a->stride;
@@ -511,28 +764,36 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
   p.Cout = a->Cout;
   p.Cout4 = (a->Cout + 3) & ~3;
   const int cout_pad = (a->Cout + 15) / 16 * 16;
+  const int J = a->ksize * a->ksize * p.chunks;
+  if (algo == 1) {
+    p.tile_w = a->tile_w > 0 ? a->tile_w : (p.Wo >= 32 ? 32 : pow2_at_least(p.Wo));
+    KB_REQUIRE(p.tile_w <= kTileM && (p.tile_w & (p.tile_w - 1)) == 0, "kb_conv2d: tile_w must be a power of two <= 128");
+    p.tile_h = kTileM / p.tile_w;
+  } else {
+    p.tile_w = kHaloTileW;
+    p.tile_h = kHaloTileH;
+  }
+  p.tiles_x = (p.Wo + p.tile_w - 1) / p.tile_w;
+  p.tiles_y = (p.Ho + p.tile_h - 1) / p.tile_h;
   const long tiles = (long)p.tiles_x * p.tiles_y * a->N;
   int npad = a->n_block > 0 ? a->n_block : cout_pad;
   if (a->n_block <= 0) {
     if (npad > 256) npad = 256;
-    // few tiles (deep, low-resolution rows): split the output channels over more CTAs to fill the 148 SMs
-    while (npad > 64 && npad % 32 == 0 && tiles * ((cout_pad + npad - 1) / npad) < 148) npad /= 2;
+    // few tiles (deep, low-resolution rows): split the output channels over more CTAs to fill the SMs
+    while (npad > 64 && npad % 32 == 0 && tiles * ((cout_pad + npad - 1) / npad) < sm_count()) npad /= 2;
   }
   KB_REQUIRE(npad % 16 == 0 && npad >= 16 && npad <= 256, "kb_conv2d: n_block must be a multiple of 16 in [16,256]");
   p.Npad = npad;
   const int n_blocks = (cout_pad + npad - 1) / npad;
-  p.tmem_cols = (uint32_t)max(32, pow2_at_least(npad));
-  const int stage_bytes = kABytes + npad * kChunk * 4;
-  const int J = a->ksize * a->ksize * p.chunks;
-  int stages = a->stages > 0 ? a->stages : (stage_bytes * 4 <= 100 * 1024 ? 4 : (200 * 1024) / stage_bytes);
-  stages = max(2, min(min(stages, 8), max(J, 2)));
-  p.stages = stages;
+  p.n_blocks = n_blocks;
   p.bias = a->bias;
   p.res = a->res;
   p.res_stride = a->res_stride;
   if (a->res) KB_REQUIRE(a->res_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(a->res) & 15) == 0, "kb_conv2d: residual alignment");
   p.n_out = a->n_out;
+  p.vec = (a->Cout % 4 == 0) && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0;
   for (int o = 0; o < a->n_out; ++o) {
+    if (reinterpret_cast<uintptr_t>(a->out[o].slope) & 15) p.vec = 0;
     KB_REQUIRE(a->out[o].ptr && a->out[o].pixel_stride % 4 == 0 && a->out[o].pixel_stride >= p.Cout4 &&
                    (reinterpret_cast<uintptr_t>(a->out[o].ptr) & 15) == 0,
                "kb_conv2d: output %d: pointer / stride must be 16-byte aligned and hold %d channels", o, p.Cout4);
@@ -541,50 +802,61 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
     p.out[o].slope = a->out[o].slope;
     p.out[o].round_tf32 = a->out[o].round_tf32;
   }
-
-  // A: NHWC activations as a 4-D tensor {C, W, H, N}; box {32, tile_w*stride, tile_h*stride, 1} traversed with the
-  // convolution stride -> tile_w x tile_h pixels x 32 channels = 128 rows of 128 bytes, 128B-swizzled.
+  int rc = raise_smem_limit();
+  if (rc) return rc;
   CUtensorMap map_a, map_b;
-  {
-    cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->N};
-    cuuint64_t strides[3] = {(cuuint64_t)a->x_stride * 4, (cuuint64_t)a->x_stride * 4 * a->W,
-                             (cuuint64_t)a->x_stride * 4 * a->W * a->H};
-    cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)(p.tile_w * a->stride), (cuuint32_t)(p.tile_h * a->stride), 1};
-    cuuint32_t estr[4] = {1, (cuuint32_t)a->stride, (cuuint32_t)a->stride, 1};
-    CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(a->x), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_error("kb_conv2d: cuTensorMapEncodeTiled(activations) failed with CUresult %d", (int)r);
-      return KB_EINVAL;
-    }
+  rc = make_weight_map(enc, a->w_packed, cout_pad, J, npad, &map_b);
+  if (rc) return rc;
+  const int b_bytes = npad * kChunk * 4;
+  const size_t smem_cap = 227 * 1024;
+
+  if (algo == 1) {
+    p.tmem_cols = (uint32_t)max(32, pow2_at_least(npad));
+    const int stage_bytes = kABytes + b_bytes;
+    int stages = a->stages > 0 ? a->stages : (stage_bytes * 4 <= 100 * 1024 ? 4 : (200 * 1024) / stage_bytes);
+    stages = max(2, min(min(stages, 8), max(J, 2)));
+    p.stages = stages;
+    rc = make_act_map(enc, a, p.tile_w * a->stride, p.tile_h * a->stride, a->stride, &map_a);
+    if (rc) return rc;
+    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16;
+    KB_REQUIRE(smem <= smem_cap, "kb_conv2d: pipeline does not fit shared memory");
+    dim3 grid((unsigned)tiles, (unsigned)n_blocks);
+    k_conv_tf32<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+    count_launch();
+    return check_launch("kb_conv2d");
   }
-  {
-    cuuint64_t dims[3] = {(cuuint64_t)kChunk, (cuuint64_t)cout_pad, (cuuint64_t)J};
-    cuuint64_t strides[2] = {(cuuint64_t)kChunk * 4, (cuuint64_t)kChunk * 4 * cout_pad};
-    cuuint32_t box[3] = {(cuuint32_t)kChunk, (cuuint32_t)npad, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(a->w_packed), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_error("kb_conv2d: cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r);
-      return KB_EINVAL;
-    }
+
+  // ---- persistent halo kernel ----
+  const int halo_w = kHaloTileW + a->ksize - 1, halo_h = kHaloTileH + a->ksize - 1;
+  p.pitch = halo_w;
+  p.debug = env_int("KB_CONV_DEBUG", 0);
+  const int box_bytes = p.pitch * halo_h * kChunk * 4;
+  p.a_stage_bytes = (box_bytes + 1023) & ~1023;
+  p.tmem_cols = (uint32_t)max(32, pow2_at_least(2 * npad));
+  KB_REQUIRE(p.tmem_cols <= 512, "kb_conv2d: accumulator does not fit TMEM");
+  const size_t fixed = 1024 + 256;   // alignment slack + barriers
+  const size_t budget = smem_cap - fixed;
+  p.resident = (n_blocks == 1 && (size_t)J * b_bytes + 2 * (size_t)p.a_stage_bytes <= budget) ? 1 : 0;
+  if (env_int("KB_CONV_NO_RESIDENT", 0)) p.resident = 0;
+  if (p.resident) {
+    p.b_stages = J;
+    p.a_stages = (int)min((size_t)6, (budget - (size_t)J * b_bytes) / p.a_stage_bytes);
+  } else {
+    p.a_stages = p.chunks >= 3 ? 3 : 2;
+    p.b_stages = (int)min((size_t)12, (budget - (size_t)p.a_stages * p.a_stage_bytes) / b_bytes);
+    KB_REQUIRE(p.b_stages >= 2, "kb_conv2d: weight ring does not fit shared memory");
   }
-  const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-    if (e != cudaSuccess) {
-      set_error("kb_conv2d: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
-    smem_set = 227 * 1024;
-  }
-  KB_REQUIRE(smem <= 227 * 1024, "kb_conv2d: pipeline does not fit shared memory");
-  dim3 grid((unsigned)tiles, (unsigned)n_blocks);
-  k_conv_tf32<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  if (a->stages > 0) p.a_stages = max(2, min(a->stages, p.a_stages));
+  KB_REQUIRE((2 * p.a_stages + 2 * p.b_stages + 4) * sizeof(uint64_t) + 16 <= 256 + 768, "kb_conv2d: too many pipeline stages");
+  p.work_items = tiles * n_blocks;
+  rc = make_act_map(enc, a, p.pitch, halo_h, 1, &map_a);
+  if (rc) return rc;
+  const size_t smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * b_bytes +
+                      (2 * p.a_stages + 2 * p.b_stages + 4) * sizeof(uint64_t) + 16;
+  KB_REQUIRE(smem <= smem_cap, "kb_conv2d: pipeline does not fit shared memory");
+  const unsigned grid = (unsigned)min((long)sm_count(), p.work_items);
+  if (a->ksize == 1) k_conv_halo_tf32<1><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  else k_conv_halo_tf32<3><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
   count_launch();
   return check_launch("kb_conv2d");
 }

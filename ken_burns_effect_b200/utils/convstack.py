@@ -78,7 +78,7 @@ def packed(conv, bn=None):
     return cached[1]
 
 
-def conv2d(x, pc, outs, res=None, crop=None, tile_w=0, n_block=0, stages=0):
+def conv2d(x, pc, outs, res=None, crop=None, tile_w=0, n_block=0, stages=0, algo=0):
     """outs: list of (slope tensor | None, round_tf32 bool, destination view | None).  Returns the output views.
     out_o = prelu_o(conv(x) + bias + res); crop=(Ho,Wo) keeps only the top-left part (reference: F.pad(..., -1))."""
     _check_act(x)
@@ -115,7 +115,7 @@ def conv2d(x, pc, outs, res=None, crop=None, tile_w=0, n_block=0, stages=0):
         a.out[i].round_tf32 = 1 if rnd else 0
         result.append(dst)
     a.out_H, a.out_W = (Ho, Wo) if crop is not None else (0, 0)
-    a.tile_w, a.n_block, a.stages = tile_w, n_block, stages
+    a.tile_w, a.n_block, a.stages, a.algo = tile_w, n_block, stages, algo
     nat.check(nat.lib().kb_conv2d(ctypes.byref(a), _stream()), "kb_conv2d")
     return result
 
