@@ -35,6 +35,8 @@ extern "C" {
 #define KB_EINVAL (-1)   /* bad argument (null pointer, non-positive size, unsupported C) */
 #define KB_ENOSUP (-2)   /* valid request this build does not support */
 
+#define KB_MAX_SIDE 4194302 /* largest image width / height (the splat rounds pixel coordinates exactly below 2^22) */
+
 typedef void *kb_stream_t; /* cudaStream_t */
 
 /* Library identification.  kb_version() = 10000*major + 100*minor + patch. */
@@ -174,6 +176,18 @@ int kb_maxpool2_ceil(const float *x, long x_stride, int N, int H, int W, int C, 
 /* Layout changes at the module boundary: y_nhwc = (x_nchw - sub) * mul ; y_nchw = x_nhwc * mul + add. */
 int kb_nchw_to_nhwc(const float *x, int N, int C, int H, int W, float *y, long y_stride, float sub, float mul, kb_stream_t stream);
 int kb_nhwc_to_nchw(const float *x, long x_stride, int N, int C, int H, int W, float *y, float mul, float add, kb_stream_t stream);
+
+/* ---- self-test ------------------------------------------------------------------------------------ */
+/* The kernels replace the fp64 sub-expressions the reference's source substitution creates (utils/common.py:453,
+ * :467-470, :556-561, :639) and the IEEE divisions of the frame tail (:686, :255) by cheaper fp32 sequences that are
+ * the same functions.  This entry point evaluates both forms on the device for n pairs (a[i], b[i]) and adds the
+ * number of disagreements to *mismatches (device, caller-zeroed):
+ *   which 0: quantised a / (|b| + 1e-7) through the shared reciprocal vs the IEEE division
+ *         1: a >= b + 1 and a <= b + 1 (exact fp32) vs the fp64 comparisons
+ *         2: floor / round-half-away of a without conversions vs floorf / roundf (|a| < 2^22)
+ *         3: a + (0.5*W - 0.5) vs the two fp64 additions; a >= 0.001f vs (double)a < 0.001; float -> double widening */
+int kb_selftest_arith(int which, const float *a, const float *b, long n, int W, unsigned long long *mismatches,
+                      kb_stream_t stream);
 
 /* ---- measurement hooks (bench.py) ---------------------------------------------------------------- */
 /* Stages of kb_render_frames, in launch order: 0 memset(accumulators) 1 init(z-buffer + resize tables)

@@ -67,6 +67,7 @@ SIGNATURES = {
     "kb_maxpool2_ceil": (c_int, [c_void, c_long, c_int, c_int, c_int, c_int, c_void, c_long, c_void]),
     "kb_nchw_to_nhwc": (c_int, [c_void, c_int, c_int, c_int, c_int, c_void, c_long, ctypes.c_float, ctypes.c_float, c_void]),
     "kb_nhwc_to_nchw": (c_int, [c_void, c_long, c_int, c_int, c_int, c_int, c_void, ctypes.c_float, ctypes.c_float, c_void]),
+    "kb_selftest_arith": (c_int, [c_int, c_void, c_void, c_long, c_int, c_void, c_void]),
     "kb_profile_enable": (c_int, [c_int]),
     "kb_profile_read": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]),
 }

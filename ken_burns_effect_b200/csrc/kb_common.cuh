@@ -35,6 +35,19 @@ static inline unsigned int cdiv(long a, long b) { return (unsigned int)((a + b -
 // contract differently from the reference's NVRTC build (whose SASS shows: FADD for num/den, a full
 // precision fp32 division, one FFMA per intersection component, DADD/DADD + F2F for ox/oy, an IEEE fp64
 // division + DADD + F2F for err).
+//
+// The reference evaluates several sub-expressions in fp64 (double literals pasted into float code).  ncu
+// showed the float<->double / float<->int conversions of a literal transcription saturating the XU pipe
+// (16 lanes/clk/SM; profiles/ncu_r01b_summary.md), so every such expression is replaced here by an fp32
+// form that is PROVABLY the same function (tests/test_exact_arith.py brute-forces each identity on the CPU):
+//   (double)z < 0.001                    ==  z < 0.001f          ((float)0.001 is the smallest float >= 0.001)
+//   (float)((double)i + 0.5*W - 0.5)     ==  i + (float)(0.5*W - 0.5)   for W >= 2: both double additions are
+//                                            exact or far below half an ulp of the result, so one fp32
+//                                            rounding of the exact sum is what the reference computes too
+//   (int)floor(o), (float)(int)          ==  magic-number rounding + fix-up, for |o| < 2^22 (farther out a
+//                                            point touches no pixel of any image this library accepts)
+//   (double)a >= (double)b + 1.0         ==  sign of the exact difference a - b - 1 (TwoSum), for 1 <= |b| <= 1e15
+// Only err keeps its fp64 division (its quotient is rounded twice; no fp32 shortcut reproduces that).
 struct Proj {
   float ox, oy, err;
   int nwx, nwy;
@@ -46,11 +59,33 @@ struct Camera {
   double fB;      // focal * baseline        -- the double constant the reference's compiler folds
   double halfW;   // 0.5 * W
   double halfH;   // 0.5 * H
+  float cx, cy;   // (float)(0.5*W - 0.5), (float)(0.5*H - 0.5): exact for W, H < 2^24
   int W, H;
 };
 
+constexpr float kFloorRange = 4194304.0f;   // 2^22; images are limited to 2^22 - 2 pixels per side
+
+// floor(v) as float and int without conversion instructions; requires |v| < 2^22.
+__device__ __forceinline__ void floor_fi(float v, float &f, int &i) {
+  const float magic = 12582912.0f;                         // 1.5 * 2^23: ulp 1 around it
+  const float r = __fadd_rn(v, magic);                     // magic + rint(v)
+  i = __float_as_int(r) - 0x4B400000;
+  f = __fsub_rn(r, magic);
+  if (f > v) {
+    f = __fsub_rn(f, 1.0f);
+    i -= 1;
+  }
+}
+
+// float -> double for a normal, finite float: pure integer work (the F2F instruction runs on the XU pipe).
+__device__ __forceinline__ double widen_normal(float v) {
+  const unsigned b = __float_as_uint(v);
+  const unsigned hi = (b & 0x80000000u) | (((b & 0x7FFFFFFFu) >> 3) + 0x38000000u);
+  return __hiloint2double((int)hi, (int)(b << 29));
+}
+
 __device__ __forceinline__ bool project(float x, float y, float z, const Camera &cam, Proj &p) {
-  if ((double)z < 0.001) return false;                       // :453 (float promoted to double)
+  if (!(z >= 0.001f)) return false;                          // :453  (double)z < 0.001; NaN is culled like there
   const float nx = __fsub_rn(0.0f, x);                       // dblLineVector = 0 - P      :451
   const float ny = __fsub_rn(0.0f, y);
   const float num = __fsub_rn(cam.f32, z);                   // dot(planePoint - P, n)     :457
@@ -59,13 +94,20 @@ __device__ __forceinline__ bool project(float x, float y, float z, const Camera 
   // :461 fabs(den) < 0.001 cannot fire once z >= 0.001 held
   const float ix = __fmaf_rn(t, nx, x);                      // P + t * lineVector         :465
   const float iy = __fmaf_rn(t, ny, y);
-  p.ox = __double2float_rn(__dadd_rn(__dadd_rn((double)ix, cam.halfW), -0.5));   // :467
-  p.oy = __double2float_rn(__dadd_rn(__dadd_rn((double)iy, cam.halfH), -0.5));   // :468
-  p.err = __double2float_rn(__dsub_rn(1000000.0, __ddiv_rn(cam.fB, __dadd_rn((double)z, 0.0000001))));  // :470
-  p.nwx = (int)floorf(p.ox);                                 // :472-479
-  p.nwy = (int)floorf(p.oy);
-  const float x0 = (float)p.nwx, x1 = (float)(p.nwx + 1);
-  const float y0 = (float)p.nwy, y1 = (float)(p.nwy + 1);
+  if (cam.W >= 2 && cam.H >= 2) {
+    p.ox = __fadd_rn(ix, cam.cx);                            // :467-468, see the identities above
+    p.oy = __fadd_rn(iy, cam.cy);
+  } else {                                                   // 1-pixel-wide images: the literal form
+    p.ox = __double2float_rn(__dadd_rn(__dadd_rn((double)ix, cam.halfW), -0.5));
+    p.oy = __double2float_rn(__dadd_rn(__dadd_rn((double)iy, cam.halfH), -0.5));
+  }
+  if (!(fabsf(p.ox) < kFloorRange && fabsf(p.oy) < kFloorRange)) return false;   // touches no pixel (also NaN)
+  const double zd = z < 3.0e38f ? widen_normal(z) : (double)z;
+  p.err = __double2float_rn(__dsub_rn(1000000.0, __ddiv_rn(cam.fB, __dadd_rn(zd, 0.0000001))));  // :470
+  float x0, y0;
+  floor_fi(p.ox, x0, p.nwx);                                 // :472-479
+  floor_fi(p.oy, y0, p.nwy);
+  const float x1 = __fadd_rn(x0, 1.0f), y1 = __fadd_rn(y0, 1.0f);   // (float)(nwx + 1): exact below 2^24
   const float ax = __fsub_rn(x1, p.ox), bx = __fsub_rn(p.ox, x0);
   const float ay = __fsub_rn(y1, p.oy), by = __fsub_rn(p.oy, y0);
   p.wnw = __fmul_rn(ax, ay);                                 // :481-484
@@ -73,6 +115,30 @@ __device__ __forceinline__ bool project(float x, float y, float z, const Camera 
   p.wsw = __fmul_rn(ax, by);
   p.wse = __fmul_rn(bx, by);
   return true;
+}
+
+// Exact sign tests of the reference's fp64 comparisons "(double)a >= (double)b + 1.0" (:556-561) and
+// "(double)a <= (double)b + 1.0" (:639).  d = fl(a - b) decides unless it is exactly 1; then TwoSum's
+// error term e (a - b = d + e exactly) does.  b + 1.0 is exact in fp64 for 1 <= |b| <= 2^52, which is what
+// makes the exact difference the reference's own result; other magnitudes take the literal form.
+__device__ __forceinline__ float twosum_err(float a, float b, float d) {   // d = fl(a - b)
+  const float bb = __fsub_rn(d, a);
+  return __fadd_rn(__fsub_rn(a, __fsub_rn(d, bb)), __fsub_rn(__fsub_rn(0.0f, b), bb));
+}
+__device__ __forceinline__ bool cmp_exact_domain(float a, float b) {
+  return (fabsf(b) >= 1.0f) & (fabsf(b) <= 1.0e15f) & (fabsf(a) <= 1.0e15f);
+}
+__device__ __forceinline__ bool ge_plus_one(float a, float b) {            // (double)a >= (double)b + 1.0
+  if (!cmp_exact_domain(a, b)) return (double)a >= __dadd_rn((double)b, 1.0);
+  const float d = __fsub_rn(a, b);
+  if (d != 1.0f) return d > 1.0f;
+  return twosum_err(a, b, d) >= 0.0f;
+}
+__device__ __forceinline__ bool le_plus_one(float a, float b) {            // (double)a <= (double)b + 1.0
+  if (!cmp_exact_domain(a, b)) return (double)a <= __dadd_rn((double)b, 1.0);
+  const float d = __fsub_rn(a, b);
+  if (d != 1.0f) return d < 1.0f;
+  return twosum_err(a, b, d) <= 0.0f;
 }
 
 // process_shift's tensor half (utils/common.py:104-109) applied to one point: the reference runs
@@ -118,7 +184,7 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 
 // The z gate of updateOutput, :639: (double)err <= (double)zee + 1.0.
 __device__ __forceinline__ bool z_gate(float err, float zee) {
-  return (double)err <= __dadd_rn((double)zee, 1.0);
+  return le_plus_one(err, zee);
 }
 
 // The 16 ray directions of fill_disocclusion (utils/common.py:859-867) after the reference's per-thread

@@ -115,12 +115,10 @@ __global__ void __launch_bounds__(256) k_degrid(const float *__restrict__ zin, f
     if ((x1 < 0) | (x1 >= W) | (y1 < 0) | (y1 >= H)) continue;
     if ((x2 < 0) | (x2 >= W) | (y2 < 0) | (y2 >= H)) continue;
     const float a = z[(long)y1 * W + x1], d = z[(long)y2 * W + x2];
-    if ((double)c >= __dadd_rn((double)a, 1.0)) {
-      if ((double)c >= __dadd_rn((double)d, 1.0)) {
-        count += 2;
-        sum = __fadd_rn(sum, a);
-        sum = __fadd_rn(sum, d);
-      }
+    if (ge_plus_one(c, a) && ge_plus_one(c, d)) {   // :556-561, exact fp32 form of the fp64 comparison (kb_common.cuh)
+      count += 2;
+      sum = __fadd_rn(sum, a);
+      sum = __fadd_rn(sum, d);
     }
   }
   float r = c;
@@ -269,6 +267,70 @@ __global__ void __launch_bounds__(256) k_median5_binary(const float *__restrict_
   out[base + (long)y * W + x] = cnt >= 13 ? 1.0f : 0.0f;
 }
 
+
+// ---- self-test of the exact fp32 replacements in kb_common.cuh / kb_frames.cu against the literal forms -----------
+__device__ __forceinline__ unsigned char st_quant(float acc, float den) {
+  float v = __fmul_rn(__fdiv_rn(acc, den), 255.0f);
+  v = fminf(fmaxf(v, 0.0f), 255.0f);
+  return (unsigned char)v;
+}
+__device__ __forceinline__ unsigned char st_quant_shared(float acc, float den) {
+  // same sequence as kb_frames.cu: quant_shared()
+  if (!((den >= 0x1p-60f) & (den <= 0x1p60f) & (fabsf(acc) <= 0x1p60f))) return st_quant(acc, den);
+  float r0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(den));
+  const float e = __fmaf_rn(-den, r0, 1.0f);
+  const float r = __fmaf_rn(r0, e, r0);
+  const float q0 = __fmul_rn(acc, r);
+  const float rem = __fmaf_rn(-den, q0, acc);
+  float v = __fmul_rn(__fmaf_rn(r, rem, q0), 255.0f);
+  v = fminf(fmaxf(v, 0.0f), 255.0f);
+  return (unsigned char)v;
+}
+__device__ __forceinline__ int st_round_away_i(float v) {
+  const float magic = 12582912.0f;
+  const float r = __fadd_rn(v, magic);
+  int i = __float_as_int(r) - 0x4B400000;
+  const float diff = __fsub_rn(v, __fsub_rn(r, magic));
+  i += ((diff == 0.5f) & (v > 0.0f)) ? 1 : 0;
+  i -= ((diff == -0.5f) & (v < 0.0f)) ? 1 : 0;
+  return i;
+}
+
+__global__ void __launch_bounds__(256) k_selftest(int which, const float *__restrict__ a, const float *__restrict__ b, long n,
+                                                  int W, unsigned long long *__restrict__ mismatches) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = a[i], y = b[i];
+  bool bad = false;
+  switch (which) {
+    case 0:   // shared-reciprocal quantisation vs IEEE division; y plays the weight sum (>= 0)
+      bad = st_quant_shared(x, __fadd_rn(fabsf(y), 0.0000001f)) != st_quant(x, __fadd_rn(fabsf(y), 0.0000001f));
+      break;
+    case 1:   // exact comparisons vs the fp64 forms
+      bad = (ge_plus_one(x, y) != ((double)x >= __dadd_rn((double)y, 1.0))) ||
+            (le_plus_one(x, y) != ((double)x <= __dadd_rn((double)y, 1.0)));
+      break;
+    case 2: { // floor / round without conversion instructions, |x| < 2^22
+      if (!(fabsf(x) < kFloorRange)) break;
+      float f;
+      int k;
+      floor_fi(x, f, k);
+      bad = (f != floorf(x)) || (k != (int)floorf(x)) || (st_round_away_i(x) != (int)roundf(x));
+      break;
+    }
+    case 3: { // pixel coordinate: fp32 sum vs the reference's two fp64 additions (W >= 2); z threshold; widen
+      const float lit = __double2float_rn(__dadd_rn(__dadd_rn((double)x, 0.5 * (double)W), -0.5));
+      bad = (W >= 2 && lit != __fadd_rn(x, (float)(0.5 * (double)W - 0.5))) || ((x >= 0.001f) != !((double)x < 0.001)) ||
+            (x >= 0.001f && x < 3.0e38f && widen_normal(x) != (double)x);
+      break;
+    }
+    default:
+      break;
+  }
+  if (bad) atomicAdd(mismatches, 1ULL);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host helpers
 // ---------------------------------------------------------------------------------------------------
@@ -279,6 +341,8 @@ Camera make_camera(double focal, double baseline, int H, int W) {
   c.fB = focal * baseline;
   c.halfW = 0.5 * (double)W;
   c.halfH = 0.5 * (double)H;
+  c.cx = (float)(0.5 * (double)W - 0.5);
+  c.cy = (float)(0.5 * (double)H - 0.5);
   c.W = W;
   c.H = H;
   return c;
@@ -319,7 +383,7 @@ int kb_shift_points(const float *xyz, const float *shift, float *out, int B, lon
 int kb_splat_min(const float *xyz, int B, long N, const float *shift_host, double focal, double baseline,
                  float *zee, int H, int W, int32_t *pix_idx, kb_stream_t stream) {
   KB_REQUIRE(xyz && zee && B > 0 && N > 0 && H > 0 && W > 0, "kb_splat_min: bad arguments");
-  KB_REQUIRE((long)H * W < (1L << 31), "kb_splat_min: image too large");
+  KB_REQUIRE((long)H * W < (1L << 31) && H <= KB_MAX_SIDE && W <= KB_MAX_SIDE, "kb_splat_min: image too large");
   cudaStream_t st = (cudaStream_t)stream;
   const long nz = (long)B * H * W;
   k_fill_f32<<<min(cdiv(nz, 256), 148u * 8u), 256, 0, st>>>(zee, nz, 1000000.0f);
@@ -343,6 +407,7 @@ int kb_splat_accum(const float *xyz, const float *data, int B, long N, int C, co
                    double focal, double baseline, const float *zee, float *accum, int H, int W,
                    kb_stream_t stream) {
   KB_REQUIRE(xyz && data && zee && accum && B > 0 && N > 0 && C > 0 && H > 0 && W > 0, "kb_splat_accum: bad arguments");
+  KB_REQUIRE((long)H * W < (1L << 31) && H <= KB_MAX_SIDE && W <= KB_MAX_SIDE, "kb_splat_accum: image too large");
   cudaStream_t st = (cudaStream_t)stream;
   const int Cp = kb_accum_channels(C);
   cudaError_t e = cudaMemsetAsync(accum, 0, sizeof(float) * (size_t)B * H * W * Cp, st);
@@ -406,6 +471,14 @@ int kb_median5_binary(const float *in, float *out, int B, int H, int W, kb_strea
   k_median5_binary<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, H, W);
   count_launch();
   return check_launch("kb_median5_binary");
+}
+
+int kb_selftest_arith(int which, const float *a, const float *b, long n, int W, unsigned long long *mismatches,
+                      kb_stream_t stream) {
+  KB_REQUIRE(a && b && mismatches && n > 0 && which >= 0 && which <= 3, "kb_selftest_arith: bad arguments");
+  k_selftest<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(which, a, b, n, W, mismatches);
+  count_launch();
+  return check_launch("kb_selftest_arith");
 }
 
 }  // extern "C"
