@@ -175,24 +175,36 @@ def main():
     pts, rgb, dep, common, poses, (cw, ch) = build_workload(args.frames, world, rank)
     N = pts.shape[1]
     F = len(poses)
+    from ken_burns_effect_b200.utils import shard
     packed_host = torch.from_numpy(np.concatenate([pts, rgb, dep], 0)).pin_memory()   # [7,N]: xyz | rgb | depth
-    packed = packed_host.to(dev) if rank == 0 else torch.empty(7, N, device=dev)
-    if world > 1:
-        dist.broadcast(packed, src=0)
+    packed = packed_host.to(dev)              # only rank 0's copy is ever read when world > 1
+    common["intWidth"], common["intHeight"] = W, H
+
+    def cloud_on_rank0():
+        c = dict(common)
+        c.update(tensorInpaPoints=packed[0:3].view(1, 3, N), tensorInpaImage=packed[3:6].view(1, 3, N),
+                 tensorInpaDepth=packed[6:7].view(1, 1, N))
+        return c
+
     renderer = kb.FrameRenderer(packed[0:3], packed[3:6], packed[6:7], W, H, BASELINE, cw, ch, batch=args.batch)
     frames_dev = torch.empty(F, H, W, 3, dtype=torch.uint8, device=dev)
     frames_host = torch.empty(F, H, W, 3, dtype=torch.uint8).pin_memory()
 
+    def exchange():
+        # the path's one exchange step (ken_burns_effect_b200/utils/shard.py): the cloud travels over NVLink once per effect
+        c = shard.broadcast_cloud(cloud_on_rank0() if rank == 0 else None, dev, src=0)
+        renderer.set_cloud(c['tensorInpaPoints'], c['tensorInpaImage'], c['tensorInpaDepth'])
+
     def step_device():
         if world > 1:
-            dist.broadcast(packed, src=0)     # the shared cloud travels over NVLink once per effect
+            exchange()
         renderer.render_into(poses, frames_dev)
 
     def step_e2e():
         if rank == 0:
             packed.copy_(packed_host, non_blocking=True)
         if world > 1:
-            dist.broadcast(packed, src=0)
+            exchange()
         renderer.render_into(poses, frames_host)
 
     def timed(fn, steps, warmup, profile=False):

@@ -11,6 +11,7 @@ import sys
 
 import cv2
 import torch
+import torch.distributed
 
 from ken_burns_effect_b200.utils.pipeline import Pipeline
 
@@ -98,8 +99,20 @@ def crop_windows(cfg, imgWidth, imgHeight):
             'objectTo': {'dblCenterU': eU, 'dblCenterV': eV, 'intCropWidth': eW, 'intCropHeight': eH}}
 
 
+def init_distributed():
+    """Under torchrun (WORLD_SIZE > 1): one process per GPU, NCCL; frames are sharded by Pipeline.__call__."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world > 1 and not torch.distributed.is_initialized():
+        local = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(local)
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.distributed.init_process_group('nccl', device_id=torch.device('cuda', local))
+    return world
+
+
 def main(argv):
     cfg = parse(argv)
+    init_distributed()
     print('Number of threads used: ', torch.get_num_threads())
     tensorImage = load_image(cfg['input_path'], cfg['pretrained_estim'])
     imgHeight, imgWidth = tensorImage.size(1), tensorImage.size(2)

@@ -249,9 +249,7 @@ class FrameRenderer:
                  batch=FRAME_BATCH):
         _need_cuda(tensorPoints, tensorImage, tensorDepth)
         self.device = tensorPoints.device
-        self.N = tensorPoints.shape[-1]
-        self.xyz = tensorPoints.reshape(3, self.N).contiguous()
-        self.rgbd = torch.cat([tensorImage.reshape(3, self.N), tensorDepth.reshape(1, self.N)], 0).contiguous()
+        self.set_cloud(tensorPoints, tensorImage, tensorDepth)
         self.H, self.W = int(intHeight), int(intWidth)
         self.batch = max(1, min(int(batch), nat.KB_MAX_POSES))
         self.params = nat.KBFrameParams(self.H, self.W, int(crop_w), int(crop_h), float(dblBaseline))
@@ -266,6 +264,19 @@ class FrameRenderer:
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.ev_rendered = [torch.cuda.Event() for _ in range(2)]
         self.ev_copied = [torch.cuda.Event() for _ in range(2)]
+
+    def set_cloud(self, tensorPoints, tensorImage, tensorDepth):
+        """Point the renderer at a (new) cloud; frame geometry and workspace are kept.  When image and depth are
+        adjacent rows of one packed [7,N] buffer (shard.unpack_cloud) nothing is copied."""
+        _need_cuda(tensorPoints, tensorImage, tensorDepth)
+        self.N = tensorPoints.shape[-1]
+        self.xyz = tensorPoints.reshape(3, self.N).contiguous()
+        img, dep = tensorImage.reshape(3, self.N), tensorDepth.reshape(1, self.N)
+        if (img.is_contiguous() and dep.is_contiguous() and dep.data_ptr() == img.data_ptr() + 12 * self.N
+                and img.untyped_storage().data_ptr() == dep.untyped_storage().data_ptr()):
+            self.rgbd = torch.as_strided(img, (4, self.N), (self.N, 1))
+        else:
+            self.rgbd = torch.cat([img, dep], 0).contiguous()
 
     def render_into(self, poses, out_frames):
         """poses: list of (shift fp32[3], focal); out_frames: uint8 tensor [len(poses),H,W,3] (device or
@@ -306,31 +317,50 @@ class FrameRenderer:
         return out_frames
 
 
-def process_kenburns(objectSettings, objectCommon, moduleInpaint):
-    """utils/common.py:172-263 -> list of uint8 [H,W,3] frames (RGB order of the input tensor's channels)."""
+def prepare_cloud(objectSettings, objectCommon, moduleInpaint):
+    """Stage A of process_kenburns, utils/common.py:175-220: reset the working cloud to the raw one and, unless in
+    dolly mode, append the points the inpainting network hallucinates at both extremes of the camera path."""
     dev = objectCommon['tensorRawPoints'].device
-    if 'boolInpaint' not in objectSettings or objectSettings['boolInpaint'] == True:  # noqa: E712
-        objectCommon['tensorInpaImage'] = objectCommon['tensorRawImage'].view(1, 3, -1)
-        objectCommon['tensorInpaDisparity'] = objectCommon['tensorRawDisparity'].view(1, 1, -1)
-        objectCommon['tensorInpaDepth'] = objectCommon['tensorRawDepth'].view(1, 1, -1)
-        objectCommon['tensorInpaPoints'] = objectCommon['tensorRawPoints'].view(1, 3, -1)
-        for dblStep in [0.0, 1.0]:
-            st, focal = _pose_settings(objectSettings, objectCommon, dblStep)
-            sx, sy, sz = _shift_scalars(st, objectCommon, focal)
-            tensorShift = torch.FloatTensor([sx, sy, sz]).view(1, 3, 1).to(dev)
-            # (the reference also renders the current cloud here, :208-215, and discards the result)
-            if not objectSettings['dolly']:
-                process_inpaint(1.1 * tensorShift, objectCommon, moduleInpaint, focal)
+    objectCommon['tensorInpaImage'] = objectCommon['tensorRawImage'].view(1, 3, -1)
+    objectCommon['tensorInpaDisparity'] = objectCommon['tensorRawDisparity'].view(1, 1, -1)
+    objectCommon['tensorInpaDepth'] = objectCommon['tensorRawDepth'].view(1, 1, -1)
+    objectCommon['tensorInpaPoints'] = objectCommon['tensorRawPoints'].view(1, 3, -1)
+    for dblStep in [0.0, 1.0]:
+        st, focal = _pose_settings(objectSettings, objectCommon, dblStep)
+        sx, sy, sz = _shift_scalars(st, objectCommon, focal)
+        tensorShift = torch.FloatTensor([sx, sy, sz]).view(1, 3, 1).to(dev)
+        # (the reference also renders the current cloud here, :208-215, and discards the result)
+        if not objectSettings['dolly']:
+            process_inpaint(1.1 * tensorShift, objectCommon, moduleInpaint, focal)
 
+
+def crop_size(objectSettings):
+    """Patch size of the per-frame getRectSubPix, utils/common.py:256."""
     f, t = objectSettings['objectFrom'], objectSettings['objectTo']
-    crop_w = max(f['intCropWidth'], t['intCropWidth'])
-    crop_h = max(f['intCropHeight'], t['intCropHeight'])
-    poses = kenburns_poses(objectSettings, objectCommon)
+    return max(f['intCropWidth'], t['intCropWidth']), max(f['intCropHeight'], t['intCropHeight'])
+
+
+def render_poses(objectSettings, objectCommon, poses, to_host=True):
+    """Stage B, utils/common.py:222-260, for the given poses of the path -> uint8 [len(poses),H,W,3]
+    (pinned host memory when to_host, else on the cloud's device)."""
+    crop_w, crop_h = crop_size(objectSettings)
     renderer = FrameRenderer(objectCommon['tensorInpaPoints'], objectCommon['tensorInpaImage'],
                              objectCommon['tensorInpaDepth'], objectCommon['intWidth'], objectCommon['intHeight'],
                              objectCommon['dblBaseline'], crop_w, crop_h)
-    host = torch.empty(len(poses), renderer.H, renderer.W, 3, dtype=torch.uint8).pin_memory()
-    renderer.render_into(poses, host)
-    torch.cuda.current_stream().synchronize()
-    frames = host.numpy()
+    if to_host:
+        out = torch.empty(len(poses), renderer.H, renderer.W, 3, dtype=torch.uint8).pin_memory()
+    else:
+        out = torch.empty(len(poses), renderer.H, renderer.W, 3, dtype=torch.uint8, device=renderer.device)
+    if len(poses):
+        renderer.render_into(poses, out)
+    torch.cuda.current_stream(renderer.device).synchronize()
+    return out
+
+
+def process_kenburns(objectSettings, objectCommon, moduleInpaint):
+    """utils/common.py:172-263 -> list of uint8 [H,W,3] frames (RGB order of the input tensor's channels)."""
+    if 'boolInpaint' not in objectSettings or objectSettings['boolInpaint'] == True:  # noqa: E712
+        prepare_cloud(objectSettings, objectCommon, moduleInpaint)
+    poses = kenburns_poses(objectSettings, objectCommon)
+    frames = render_poses(objectSettings, objectCommon, poses).numpy()
     return [frames[i] for i in range(len(poses))]

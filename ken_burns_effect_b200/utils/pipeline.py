@@ -18,7 +18,8 @@ from ..models.disparity_refinement import Refine
 from ..models.disparity_refinement_pretrained import Refine as RefineP
 from ..models.partial_inpainting import Inpaint as PartialInpaint
 from ..models.pointcloud_inpainting import Inpaint
-from .common import depth_to_points, process_kenburns
+from . import shard
+from .common import depth_to_points, kenburns_poses, prepare_cloud, process_kenburns, render_poses
 from .utils import device, load_models, resize_image
 
 
@@ -73,14 +74,31 @@ class Pipeline():
 
     @torch.no_grad()
     def __call__(self, tensorImage, zoom_settings, output_path=None, inpaint_depth=False, pretrained_estim=False):
-        self.estimate_depth(tensorImage)
-        numpyResult = process_kenburns({
+        settings = {
             'dblSteps': np.linspace(0.0, 1.0, self.frames).tolist(),
             'objectFrom': zoom_settings['objectFrom'],
             'objectTo': zoom_settings['objectTo'],
             'boolInpaint': True,
             'dolly': self.dolly,
-        }, self.objectCommon, self.moduleInpaint)
+        }
+        rank, world = shard.world()
+        if world == 1:
+            self.estimate_depth(tensorImage)
+            numpyResult = process_kenburns(settings, self.objectCommon, self.moduleInpaint)
+        else:
+            # one process per GPU (torchrun): rank 0 runs the CNN stage, the cloud is broadcast once, every rank
+            # renders its interleaved share of the poses, rank 0 gathers and writes
+            dev = torch.device('cuda', torch.cuda.current_device())
+            if rank == 0:
+                self.estimate_depth(tensorImage)
+                prepare_cloud(settings, self.objectCommon, self.moduleInpaint)
+            cloud = shard.broadcast_cloud(self.objectCommon if rank == 0 else None, dev, src=0)
+            poses = kenburns_poses(settings, cloud)
+            frames = shard.render_sharded(poses, lambda mine: render_poses(settings, cloud, mine, to_host=False))
+            if rank != 0:
+                return None
+            frames = frames.cpu().numpy()
+            numpyResult = [frames[i] for i in range(len(poses))]
 
         if self.output_frames and output_path is not None:
             frames_dir = os.path.join(output_path, 'frames')

@@ -1,11 +1,14 @@
 """Checkpoint I/O and image resize -- mirrors of utils/utils.py:60-73 (resize_image), :190-198 (save_model),
 :202-217 (load_models).  The .tar format is kept byte-compatible: torch.save of
 {nb_iter, model_state_dict, optimizer_<type>_state_dict, scheduler_<type>_state_dict}."""
+import os
+
 import torch
 import torch.nn.functional as F
 
 cuda = torch.cuda.is_available()
-device = "cuda:0" if cuda else "cpu"
+# the reference pins cuda:0 (utils/utils.py:17-18); under torchrun every process owns the GPU of its LOCAL_RANK
+device = ("cuda:%d" % int(os.environ.get("LOCAL_RANK", "0"))) if cuda else "cpu"
 
 
 def resize_image(tensorImage, max_size=512):

@@ -1,0 +1,50 @@
+"""Worker of tests/test_gpu_multirank.py (launched by torchrun, one process per GPU): the frames of a sharded effect,
+gathered on rank 0, must equal the frames rank 0 renders alone from the same cloud -- byte for byte outside the pixels
+that fp32 atomic summation order can move by one."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from ken_burns_effect_b200.utils import common as kb   # noqa: E402
+from ken_burns_effect_b200.utils import shard, synthetic   # noqa: E402
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    rank, world = shard.world()
+    W, H, focal = 256, 192, 128.0
+    zoom = synthetic.default_zoom(W, H)
+    settings = {'dblSteps': np.linspace(0, 1, 11).tolist(), 'objectFrom': zoom['objectFrom'], 'objectTo': zoom['objectTo'],
+                'dolly': False}
+    common = None
+    if rank == 0:
+        pts, rgb, dep, common = synthetic.scene_cloud(W, H, focal=focal, extra_points=3001)
+        common.update(intWidth=W, intHeight=H,
+                      tensorInpaPoints=torch.from_numpy(pts).to(dev).view(1, 3, -1),
+                      tensorInpaImage=torch.from_numpy(rgb).to(dev).view(1, 3, -1),
+                      tensorInpaDepth=torch.from_numpy(dep).to(dev).view(1, 1, -1))
+    cloud = shard.broadcast_cloud(common, dev, src=0)
+    poses = kb.kenburns_poses(settings, cloud)
+    frames = shard.render_sharded(poses, lambda mine: kb.render_poses(settings, cloud, mine, to_host=False))
+    ok = True
+    if rank == 0:
+        alone = kb.render_poses(settings, cloud, poses, to_host=False)
+        d = (frames.short() - alone.short()).abs()
+        ok = frames.shape == alone.shape and int(d.max()) <= 2 and float((d > 0).float().mean()) < 1e-3
+        print(f"multirank: world {world}, frames {tuple(frames.shape)}, max diff {int(d.max())}, differing {float((d > 0).float().mean()):.2e}")
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

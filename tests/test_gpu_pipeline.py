@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 def test_pipeline_dolly_runs_and_matches_frame_oracle():
     """Dolly mode (no inpainting stage): CNN depth on the GPU, then frames; the frame loop is checked
-    against the oracle on the very cloud the GPU pipeline produced (exact bar: <=1 per byte)."""
+    against the oracle on the very cloud the GPU pipeline produced (bar: summation-order noise only)."""
     torch.manual_seed(0)
     W, H = 384, 320
     img, _ = synthetic.synthetic_scene(W, H, seed=5)
@@ -39,7 +39,11 @@ def test_pipeline_dolly_runs_and_matches_frame_oracle():
     for i, (sh, f) in enumerate(poses):
         ref = oracle.frame(oracle.shift_points(pts, sh), data, W, H, f, oc['dblBaseline'], cw, ch)
         d = np.abs(frames[i].astype(np.int16) - ref.astype(np.int16))
-        assert d.max() <= 1 and (d > 0).mean() < 1e-3
+        # fp32 atomicAdd order (unspecified in the reference too, common.py:641) moves a render byte by at most 1 at a few
+        # pixels; OpenCV's fixed-point resize ((x + 2) >> 2 after two truncated products) can turn +1 on its four taps
+        # into +2 on rare outputs, never more
+        assert d.max() <= 2 and (d > 1).mean() < 1e-5 and (d > 0).mean() < 1e-3, \
+            f"frame {i}: max {d.max()}, differing bytes {(d > 0).mean():.2e}, >1: {(d > 1).sum()}"
 
 
 def test_pipeline_with_inpainting_grows_the_cloud():
