@@ -170,6 +170,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL logs to stdout by default; stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     pts, rgb, dep, common, poses, (cw, ch) = build_workload(args.frames, world, rank)

@@ -97,17 +97,22 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// 32 lanes x 16 consecutive fp32 columns: thread l of the warp receives row (lane base + l).
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+// 32 lanes x 16 consecutive fp32 columns: thread l of the warp receives row (lane base + l).  The load is asynchronous:
+// the registers are valid after tmem_ld_wait(), which lets the caller put other loads in flight in between.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+  // the "+r" ties make every use of r[] depend on the wait
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
 }
 
 // K-major, 128-byte swizzled operand tile whose rows are 128 bytes: 8-row groups are 1024 bytes apart.
@@ -141,6 +146,7 @@ struct ConvKernelParams {
   int tile_w, tile_h, tiles_x, tiles_y;
   int chunks, ksize, stride, pad;
   int Cout, Cout4;      // real output channels, and rounded up to 4 (allocated)
+  int cpad;             // Cout rounded up to a whole number of N blocks (size of the epilogue tables in shared memory)
   int Npad;             // UMMA N of this launch
   int stages;
   uint32_t tmem_cols;
@@ -154,6 +160,7 @@ struct ConvKernelParams {
   int pitch;            // halo row pitch in pixels (>= tile_w + ksize - 1)
   int a_stage_bytes;    // one halo slice (32 channels), rounded up to 1024
   int a_stages, b_stages;
+  int epi_off;          // byte offset of the epilogue tables from the aligned shared-memory base
   int resident;         // all weight panels stay in shared memory for the life of the CTA
   int n_blocks;
   long work_items;      // tiles * n_blocks
@@ -166,58 +173,102 @@ struct ConvKernelParams {
 // share a tile: warp e reads TMEM lanes 32*(e%4).. and the 16-column chunks of parity e/4.
 // Channels Cout..round_up(Cout,4) come out as exact zeros without masking: their filter rows and bias are zero padding
 // and the residual's own padding channels are zero by the same rule.
-__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
-
-__device__ __forceinline__ float4 ld_tail(const float *p, int c, int C) {   // p[c..c+3] with zeros beyond C
-  float4 r;
-  r.x = c < C ? __ldg(p + c) : 0.f;
-  r.y = c + 1 < C ? __ldg(p + c + 1) : 0.f;
-  r.z = c + 2 < C ? __ldg(p + c + 2) : 0.f;
-  r.w = c + 3 < C ? __ldg(p + c + 3) : 0.f;
-  return r;
-}
-
+//
+// ncu (profiles/ncu_conv_r01f_*): with bias / PReLU slopes read from global memory inside the loop, the eight epilogue
+// warps spent the tile waiting on those (L2-latency) loads and the kernel ran epilogue-bound at 14-35 % tensor-pipe
+// activity.  They now live in shared memory (staged once per CTA, zero-padded so every read is an unconditional float4),
+// the residual of a chunk is requested BEFORE the accumulator is waited for, and the TMEM load overlaps both.
 __device__ __forceinline__ float prelu1(float v, float s) { return fmaxf(v, 0.f) + s * fminf(v, 0.f); }
 
-__device__ __forceinline__ void epilogue_rows(const ConvKernelParams &p, uint32_t taddr, int img, int oy, int ox, int n0, int half) {
-  const bool inside = (oy < p.Ho) & (ox < p.Wo);
-  const long pix = inside ? ((long)img * p.Ho + oy) * p.Wo + ox : 0;
-  const float *res = p.res ? p.res + pix * p.res_stride : nullptr;
-  float *dst[kMaxOut];
+struct EpiSmem {
+  const float *bias;              // [cpad]   (zeros when the layer has no bias)
+  const float *slope[kMaxOut];    // [cpad]   (only valid where p.out[o].slope != nullptr)
+};
+
+// floats of shared memory the epilogue tables take for `cpad` (padded) output channels
+__host__ __device__ constexpr int epi_smem_floats(int cpad) { return (1 + kMaxOut) * cpad; }
+
+// Called by all 256 epilogue threads (tid 0..255) before their first tile; ends with a barrier among them.
+__device__ __forceinline__ EpiSmem epi_stage(const ConvKernelParams &p, float *base, int cpad, int tid) {
+  EpiSmem e;
+  e.bias = base;
+  for (int c = tid; c < cpad; c += 256) base[c] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
 #pragma unroll
-  for (int o = 0; o < kMaxOut; ++o) dst[o] = o < p.n_out ? p.out[o].ptr + pix * p.out[o].stride : nullptr;
-  const bool vec = p.vec != 0;
+  for (int o = 0; o < kMaxOut; ++o) {
+    float *dst = base + (1 + o) * cpad;
+    e.slope[o] = dst;
+    if (o < p.n_out && p.out[o].slope)
+      for (int c = tid; c < cpad; c += 256) dst[c] = c < p.Cout ? __ldg(p.out[o].slope + c) : 1.f;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  return e;
+}
+
+struct EpiPixel {
+  bool inside;
+  const float *res;
+  float *dst[kMaxOut];
+};
+
+__device__ __forceinline__ EpiPixel epi_pixel(const ConvKernelParams &p, int img, int oy, int ox) {
+  EpiPixel e;
+  e.inside = (oy < p.Ho) & (ox < p.Wo);
+  const long pix = e.inside ? ((long)img * p.Ho + oy) * p.Wo + ox : 0;
+  e.res = p.res ? p.res + pix * p.res_stride : nullptr;
+#pragma unroll
+  for (int o = 0; o < kMaxOut; ++o) e.dst[o] = o < p.n_out ? p.out[o].ptr + pix * p.out[o].stride : nullptr;
+  return e;
+}
+
+__device__ __forceinline__ void epi_load_res(const ConvKernelParams &p, const EpiPixel &px, int c, float4 (&rr)[4]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    rr[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (px.res && px.inside && c + 4 * g < p.Cout4) rr[g] = *reinterpret_cast<const float4 *>(px.res + c + 4 * g);
+  }
+}
+
+// The residual of the FIRST chunk must already be in rr (epi_load_res before the accumulator barrier).
+__device__ __forceinline__ void epilogue_rows(const ConvKernelParams &p, const EpiSmem &es, const EpiPixel &px, uint32_t taddr,
+                                              int n0, int half, float4 (&rr)[4]) {
   for (int c0 = 16 * half; c0 < p.Npad; c0 += 32) {
     if (n0 + c0 >= p.Cout4) break;           // warp-uniform
-    float v[16];
-    tmem_ld16(taddr + (uint32_t)c0, v);
-    if (!inside) continue;
+    uint32_t raw[16];
+    tmem_ld16_issue(taddr + (uint32_t)c0, raw);
+    float4 rnext[4];
+    const bool more = (c0 + 32 < p.Npad) && (n0 + c0 + 32 < p.Cout4);
+    if (more) epi_load_res(p, px, n0 + c0 + 32, rnext);
+    float4 bs[4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int c = n0 + c0 + 4 * g;
-      if (c >= p.Cout4) break;
-      float4 a = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-      if (p.bias) {
-        const float4 b = vec ? ldg4(p.bias + c) : ld_tail(p.bias, c, p.Cout);
-        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-      }
-      if (res) {
-        const float4 rr = *reinterpret_cast<const float4 *>(res + c);
-        a.x += rr.x; a.y += rr.y; a.z += rr.z; a.w += rr.w;
-      }
+    for (int g = 0; g < 4; ++g) bs[g] = *reinterpret_cast<const float4 *>(es.bias + n0 + c0 + 4 * g);
+    tmem_ld_wait(raw);
+    if (px.inside) {
 #pragma unroll
-      for (int o = 0; o < kMaxOut; ++o) {
-        if (o >= p.n_out) break;
-        float4 w = a;
-        if (p.out[o].slope) {
-          const float4 sl = vec ? ldg4(p.out[o].slope + c) : ld_tail(p.out[o].slope, c, p.Cout);
-          w.x = prelu1(w.x, sl.x); w.y = prelu1(w.y, sl.y); w.z = prelu1(w.z, sl.z); w.w = prelu1(w.w, sl.w);
+      for (int g = 0; g < 4; ++g) {
+        const int c = n0 + c0 + 4 * g;
+        if (c >= p.Cout4) break;
+        float4 a = make_float4(__uint_as_float(raw[4 * g]), __uint_as_float(raw[4 * g + 1]), __uint_as_float(raw[4 * g + 2]),
+                               __uint_as_float(raw[4 * g + 3]));
+        a.x += bs[g].x; a.y += bs[g].y; a.z += bs[g].z; a.w += bs[g].w;
+        a.x += rr[g].x; a.y += rr[g].y; a.z += rr[g].z; a.w += rr[g].w;
+#pragma unroll
+        for (int o = 0; o < kMaxOut; ++o) {
+          if (o >= p.n_out) break;
+          float4 w = a;
+          if (p.out[o].slope) {
+            const float4 sl = *reinterpret_cast<const float4 *>(es.slope[o] + c);
+            w.x = prelu1(w.x, sl.x); w.y = prelu1(w.y, sl.y); w.z = prelu1(w.z, sl.z); w.w = prelu1(w.w, sl.w);
+          }
+          if (p.out[o].round_tf32) {
+            w.x = round_tf32(w.x); w.y = round_tf32(w.y); w.z = round_tf32(w.z); w.w = round_tf32(w.w);
+          }
+          if (!(p.debug & 1)) *reinterpret_cast<float4 *>(px.dst[o] + c) = w;
         }
-        if (p.out[o].round_tf32) {
-          w.x = round_tf32(w.x); w.y = round_tf32(w.y); w.z = round_tf32(w.z); w.w = round_tf32(w.w);
-        }
-        if (!(p.debug & 1)) *reinterpret_cast<float4 *>(dst[o] + c) = w;
       }
+    }
+    if (more) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) rr[g] = rnext[g];
     }
   }
 }
@@ -234,6 +285,7 @@ __global__ void __launch_bounds__(kConvThreads) k_conv_tf32(const __grid_constan
   uint64_t *empty = full + p.stages;
   uint64_t *acc_full = empty + p.stages;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+  float *epi_tab = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // tile -> (image, y0, x0)
@@ -312,9 +364,13 @@ __global__ void __launch_bounds__(kConvThreads) k_conv_tf32(const __grid_constan
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int m = q * 32 + lane;               // accumulator row = pixel of the tile
     const int py = m / p.tile_w, px = m - py * p.tile_w;
+    const EpiSmem es = epi_stage(p, epi_tab, p.cpad, threadIdx.x - 64);
+    const EpiPixel ep = epi_pixel(p, img, y0 + py, x0 + px);
+    float4 rr[4];
+    epi_load_res(p, ep, n0 + 16 * half, rr);
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    epilogue_rows(p, tmem_base + ((uint32_t)(q * 32) << 16), img, y0 + py, x0 + px, n0, half);
+    epilogue_rows(p, es, ep, tmem_base + ((uint32_t)(q * 32) << 16), n0, half, rr);
   }
   tc_fence_before();
   __syncthreads();
@@ -360,6 +416,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
   uint64_t *acc_full = b_empty + p.b_stages;
   uint64_t *acc_empty = acc_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+  float *epi_tab = reinterpret_cast<float *>(smem + p.epi_off);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -459,6 +516,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int m = q * 32 + lane;
     const int py = m / kHaloTileW, px = m - py * kHaloTileW;
+    const EpiSmem es = epi_stage(p, epi_tab, p.cpad, threadIdx.x - 64);
     uint32_t as = 0, phacc = 0;
     for (long w = blockIdx.x; w < p.work_items; w += gridDim.x) {
       const int nb = (int)(w % p.n_blocks);
@@ -467,10 +525,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
       t /= p.tiles_x;
       const int ty = (int)(t % p.tiles_y);
       const int img = (int)(t / p.tiles_y);
+      const EpiPixel ep = epi_pixel(p, img, ty * kHaloTileH + py, tx * kHaloTileW + px);
+      float4 rr[4];
+      epi_load_res(p, ep, nb * p.Npad + 16 * half, rr);        // in flight while the MMAs of this tile finish
       mbar_wait(acc_full + as, phacc);
       tc_fence_after();
-      epilogue_rows(p, tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.Npad, img, ty * kHaloTileH + py,
-                    tx * kHaloTileW + px, nb * p.Npad, half);
+      epilogue_rows(p, es, ep, tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.Npad, nb * p.Npad, half, rr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
@@ -809,16 +869,18 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
   if (rc) return rc;
   const int b_bytes = npad * kChunk * 4;
   const size_t smem_cap = 227 * 1024;
+  p.cpad = n_blocks * npad;
+  const size_t epi_bytes = sizeof(float) * (size_t)epi_smem_floats(p.cpad);
 
   if (algo == 1) {
     p.tmem_cols = (uint32_t)max(32, pow2_at_least(npad));
     const int stage_bytes = kABytes + b_bytes;
-    int stages = a->stages > 0 ? a->stages : (stage_bytes * 4 <= 100 * 1024 ? 4 : (200 * 1024) / stage_bytes);
+    int stages = a->stages > 0 ? a->stages : (stage_bytes * 4 <= 100 * 1024 ? 4 : (int)((200 * 1024 - epi_bytes) / stage_bytes));
     stages = max(2, min(min(stages, 8), max(J, 2)));
     p.stages = stages;
     rc = make_act_map(enc, a, p.tile_w * a->stride, p.tile_h * a->stride, a->stride, &map_a);
     if (rc) return rc;
-    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16;
+    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 32 + epi_bytes;
     KB_REQUIRE(smem <= smem_cap, "kb_conv2d: pipeline does not fit shared memory");
     dim3 grid((unsigned)tiles, (unsigned)n_blocks);
     k_conv_tf32<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
@@ -834,7 +896,8 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
   p.a_stage_bytes = (box_bytes + 1023) & ~1023;
   p.tmem_cols = (uint32_t)max(32, pow2_at_least(2 * npad));
   KB_REQUIRE(p.tmem_cols <= 512, "kb_conv2d: accumulator does not fit TMEM");
-  const size_t fixed = 1024 + 256;   // alignment slack + barriers
+  const size_t bar_bytes = 1024;                         // barriers + TMEM slot
+  const size_t fixed = 1024 + bar_bytes + epi_bytes;     // alignment slack + barriers + epilogue tables
   const size_t budget = smem_cap - fixed;
   p.resident = (n_blocks == 1 && (size_t)J * b_bytes + 2 * (size_t)p.a_stage_bytes <= budget) ? 1 : 0;
   if (env_int("KB_CONV_NO_RESIDENT", 0)) p.resident = 0;
@@ -847,12 +910,12 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
     KB_REQUIRE(p.b_stages >= 2, "kb_conv2d: weight ring does not fit shared memory");
   }
   if (a->stages > 0) p.a_stages = max(2, min(a->stages, p.a_stages));
-  KB_REQUIRE((2 * p.a_stages + 2 * p.b_stages + 4) * sizeof(uint64_t) + 16 <= 256 + 768, "kb_conv2d: too many pipeline stages");
+  KB_REQUIRE((2 * p.a_stages + 2 * p.b_stages + 4) * sizeof(uint64_t) + 16 <= bar_bytes, "kb_conv2d: too many pipeline stages");
+  p.epi_off = (int)((size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * b_bytes + bar_bytes);
   p.work_items = tiles * n_blocks;
   rc = make_act_map(enc, a, p.pitch, halo_h, 1, &map_a);
   if (rc) return rc;
-  const size_t smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * b_bytes +
-                      (2 * p.a_stages + 2 * p.b_stages + 4) * sizeof(uint64_t) + 16;
+  const size_t smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * b_bytes + bar_bytes + epi_bytes;
   KB_REQUIRE(smem <= smem_cap, "kb_conv2d: pipeline does not fit shared memory");
   const unsigned grid = (unsigned)min((long)sm_count(), p.work_items);
   if (a->ksize == 1) k_conv_halo_tf32<1><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
