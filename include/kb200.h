@@ -138,6 +138,8 @@ typedef struct kb_conv_out {
   long pixel_stride;     /* floats, multiple of 4, >= round_up(Cout,4); channels Cout..round_up(Cout,4) are written as 0 */
   const float *slope;    /* per-channel PReLU weight applied to THIS output (NULL: none) -- the activation that
                             precedes the consumer's convolution ('relu-conv-relu-conv', pointcloud_inpainting.py:12-17) */
+  const float *mul;      /* optional [N,Ho,Wo] per-pixel factor applied last: the {0,1} mask a PartialConv2d consumer multiplies
+                            its input with (utils/partial_conv.py:71: conv(input * mask)) */
   int round_tf32;        /* 1: round to TF32 (value is only ever read by another convolution) */
   int _pad;
 } kb_conv_out;
@@ -151,6 +153,8 @@ typedef struct kb_conv_args {
   int Cout, ksize, stride, pad;   /* ksize 1..7, stride 1 or 2 */
   const float *res;      /* optional tensor added before the outputs' PReLUs (residual / GridNet skip sum), [N,Ho,Wo,res_stride] */
   long res_stride;
+  const float *pc_ratio; /* PartialConv2d (utils/partial_conv.py:62-77): per-pixel mask_ratio and update_mask [N,Ho,Wo] from */
+  const float *pc_um;    /* kb_pconv_mask; the conv output becomes ((conv + b - b) * ratio + b) * update_mask.  NULL: dense conv */
   int n_out;             /* 1..3 */
   kb_conv_out out[3];
   int out_H, out_W;      /* 0 = the convolution's own output size; smaller: only the top-left out_H x out_W pixels exist in
@@ -161,13 +165,19 @@ typedef struct kb_conv_args {
   int algo;              /* 0 = auto; 1 = one TMA load per filter tap (any filter); 2 = persistent halo kernel (stride 1, k <= 3) */
 } kb_conv_args;
 
-/* out_o = prelu_o(conv(x, w) + bias + res)   for o < n_out;  one launch. */
+/* out_o = prelu_o(pc(conv(x, w) + bias) + res) * mul_o   for o < n_out;  one launch. */
 int kb_conv2d(const kb_conv_args *args, kb_stream_t stream);
 
 /* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) followed by the block's first PReLU
  * (models/pointcloud_inpainting.py:70-72); the output may be cropped to Ho x Wo (the reference's F.pad(-1), :154-155). */
 int kb_upsample2x_prelu(const float *x, long x_stride, int N, int H, int W, int C, const float *slope, float *y, long y_stride,
-                        int Ho, int Wo, int round_tf32, kb_stream_t stream);
+                        int Ho, int Wo, int round_tf32, const float *mul /* optional [N,Ho,Wo] factor, as kb_conv_out.mul */,
+                        kb_stream_t stream);
+/* Mask bookkeeping of PartialConv2d(multi_channel=True), utils/partial_conv.py:43-69, for masks whose channels are identical
+ * (all masks of models/partial_inpainting.py): mask [N,H,W] of {0,1} (NULL = no mask = ones) ->
+ * update_mask = clamp(Cin * box_k(mask), 0, 1) and ratio = Cin*k*k / (Cin * box_k(mask) + 1e-8) * update_mask, both [N,Ho,Wo]. */
+int kb_pconv_mask(const float *mask, int N, int H, int W, int Cin, int ksize, int stride, int pad, float *ratio, float *update_mask,
+                  kb_stream_t stream);
 /* y = prelu(x) per channel (slope NULL: strided copy). */
 int kb_prelu_nhwc(const float *x, long x_stride, long pixels, int C, const float *slope, float *y, long y_stride, int round_tf32,
                   kb_stream_t stream);

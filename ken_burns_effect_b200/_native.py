@@ -28,13 +28,14 @@ class KBFrameParams(ctypes.Structure):
 
 
 class KBConvOut(ctypes.Structure):
-    _fields_ = [("ptr", c_void), ("pixel_stride", c_long), ("slope", c_void), ("round_tf32", c_int), ("_pad", c_int)]
+    _fields_ = [("ptr", c_void), ("pixel_stride", c_long), ("slope", c_void), ("mul", c_void), ("round_tf32", c_int), ("_pad", c_int)]
 
 
 class KBConvArgs(ctypes.Structure):
     _fields_ = [("x", c_void), ("N", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("x_stride", c_long),
                 ("w_packed", c_void), ("bias", c_void), ("Cout", c_int), ("ksize", c_int), ("stride", c_int),
-                ("pad", c_int), ("res", c_void), ("res_stride", c_long), ("n_out", c_int), ("out", KBConvOut * 3),
+                ("pad", c_int), ("res", c_void), ("res_stride", c_long), ("pc_ratio", c_void), ("pc_um", c_void), ("n_out", c_int),
+                ("out", KBConvOut * 3),
                 ("out_H", c_int), ("out_W", c_int), ("tile_w", c_int), ("n_block", c_int), ("stages", c_int), ("algo", c_int)]
 
 
@@ -62,7 +63,8 @@ SIGNATURES = {
     "kb_conv_pack_weights": (c_int, [c_void, c_int, c_int, c_int, c_void, c_void, c_void]),
     "kb_conv2d": (c_int, [ctypes.POINTER(KBConvArgs), c_void]),
     "kb_upsample2x_prelu": (c_int, [c_void, c_long, c_int, c_int, c_int, c_int, c_void, c_void, c_long, c_int, c_int,
-                                    c_int, c_void]),
+                                    c_int, c_void, c_void]),
+    "kb_pconv_mask": (c_int, [c_void, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void, c_void, c_void]),
     "kb_prelu_nhwc": (c_int, [c_void, c_long, c_long, c_int, c_void, c_void, c_long, c_int, c_void]),
     "kb_maxpool2_ceil": (c_int, [c_void, c_long, c_int, c_int, c_int, c_int, c_void, c_long, c_void]),
     "kb_nchw_to_nhwc": (c_int, [c_void, c_int, c_int, c_int, c_int, c_void, c_long, ctypes.c_float, ctypes.c_float, c_void]),

@@ -138,6 +138,7 @@ struct ConvOut {
   float *ptr;
   long stride;          // floats per pixel
   const float *slope;   // per-channel PReLU applied to this output (nullptr = identity)
+  const float *mul;     // per-pixel factor applied last (the {0,1} mask a partial-conv consumer multiplies its input with)
   int round_tf32;       // round to TF32 (the value only feeds convolutions)
 };
 
@@ -153,6 +154,8 @@ struct ConvKernelParams {
   const float *bias;
   const float *res;
   long res_stride;
+  const float *pc_ratio;   // partial convolution (utils/partial_conv.py:62-77): per-pixel mask_ratio and update_mask, or nullptr
+  const float *pc_um;
   int n_out;
   int vec;              // bias / slope arrays can be read as float4 (Cout % 4 == 0, 16-byte aligned)
   ConvOut out[kMaxOut];
@@ -208,6 +211,8 @@ struct EpiPixel {
   bool inside;
   const float *res;
   float *dst[kMaxOut];
+  float ratio, um;        // partial-conv scalars of this pixel (1, 1 for a dense convolution)
+  float mul[kMaxOut];     // trailing per-pixel factor of each output (1 = none)
 };
 
 __device__ __forceinline__ EpiPixel epi_pixel(const ConvKernelParams &p, int img, int oy, int ox) {
@@ -215,8 +220,13 @@ __device__ __forceinline__ EpiPixel epi_pixel(const ConvKernelParams &p, int img
   e.inside = (oy < p.Ho) & (ox < p.Wo);
   const long pix = e.inside ? ((long)img * p.Ho + oy) * p.Wo + ox : 0;
   e.res = p.res ? p.res + pix * p.res_stride : nullptr;
+  e.ratio = p.pc_ratio ? __ldg(p.pc_ratio + pix) : 1.f;      // requested here, consumed after the accumulator barrier
+  e.um = p.pc_um ? __ldg(p.pc_um + pix) : 1.f;
 #pragma unroll
-  for (int o = 0; o < kMaxOut; ++o) e.dst[o] = o < p.n_out ? p.out[o].ptr + pix * p.out[o].stride : nullptr;
+  for (int o = 0; o < kMaxOut; ++o) {
+    e.dst[o] = o < p.n_out ? p.out[o].ptr + pix * p.out[o].stride : nullptr;
+    e.mul[o] = (o < p.n_out && p.out[o].mul) ? __ldg(p.out[o].mul + pix) : 1.f;
+  }
   return e;
 }
 
@@ -250,6 +260,13 @@ __device__ __forceinline__ void epilogue_rows(const ConvKernelParams &p, const E
         float4 a = make_float4(__uint_as_float(raw[4 * g]), __uint_as_float(raw[4 * g + 1]), __uint_as_float(raw[4 * g + 2]),
                                __uint_as_float(raw[4 * g + 3]));
         a.x += bs[g].x; a.y += bs[g].y; a.z += bs[g].z; a.w += bs[g].w;
+        if (p.pc_ratio) {
+          // output = ((raw_out - bias) * mask_ratio + bias) * update_mask, utils/partial_conv.py:74-77, same operation order
+          a.x = __fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(a.x, bs[g].x), px.ratio), bs[g].x), px.um);
+          a.y = __fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(a.y, bs[g].y), px.ratio), bs[g].y), px.um);
+          a.z = __fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(a.z, bs[g].z), px.ratio), bs[g].z), px.um);
+          a.w = __fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(a.w, bs[g].w), px.ratio), bs[g].w), px.um);
+        }
         a.x += rr[g].x; a.y += rr[g].y; a.z += rr[g].z; a.w += rr[g].w;
 #pragma unroll
         for (int o = 0; o < kMaxOut; ++o) {
@@ -258,6 +275,9 @@ __device__ __forceinline__ void epilogue_rows(const ConvKernelParams &p, const E
           if (p.out[o].slope) {
             const float4 sl = *reinterpret_cast<const float4 *>(es.slope[o] + c);
             w.x = prelu1(w.x, sl.x); w.y = prelu1(w.y, sl.y); w.z = prelu1(w.z, sl.z); w.w = prelu1(w.w, sl.w);
+          }
+          if (p.out[o].mul) {
+            w.x *= px.mul[o]; w.y *= px.mul[o]; w.z *= px.mul[o]; w.w *= px.mul[o];
           }
           if (p.out[o].round_tf32) {
             w.x = round_tf32(w.x); w.y = round_tf32(w.y); w.z = round_tf32(w.z); w.w = round_tf32(w.w);
@@ -570,7 +590,7 @@ __global__ void __launch_bounds__(256) k_pack_weights(const float *__restrict__ 
 // (models/pointcloud_inpainting.py:70-72); output optionally cropped to (Ho, Wo) <= (2H, 2W).
 __global__ void __launch_bounds__(256) k_upsample2x_prelu(const float *__restrict__ x, long xs, int H, int W, int C4,
                                                           const float *__restrict__ slope, int C, float *__restrict__ y, long ys,
-                                                          int Ho, int Wo, int round, long total) {
+                                                          int Ho, int Wo, int round, long total, const float *__restrict__ mul) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int cg = (int)(i % C4);
@@ -600,6 +620,7 @@ __global__ void __launch_bounds__(256) k_upsample2x_prelu(const float *__restric
     const int c = 4 * cg + e;
     if (slope && c < C) v = v > 0.f ? v : v * __ldg(slope + c);
     if (c >= C) v = 0.f;
+    if (mul) v *= __ldg(mul + ((long)n * Ho + oy) * Wo + ox);
     o[e] = round ? round_tf32(v) : v;
   }
   *reinterpret_cast<float4 *>(y + (((long)n * Ho + oy) * Wo + ox) * ys + 4 * cg) = make_float4(o[0], o[1], o[2], o[3]);
@@ -676,6 +697,40 @@ __global__ void __launch_bounds__(256) k_nhwc_to_nchw(const float *__restrict__ 
   const int c = (int)(r % C);
   const int n = (int)(r / C);
   y[i] = x[((long)n * HW + pix) * xs + c] * mul + add;
+}
+
+
+// ---- PartialConv2d mask bookkeeping, utils/partial_conv.py:43-69 --------------------------------------------------------
+// With multi_channel=True the reference convolves a [N,Cin,H,W] mask with an all-ones [Cout,Cin,k,k] filter.  Every mask of
+// models/partial_inpainting.py has identical channels (it starts as tensorMasks.expand_as(data), :152, and each update
+// is again channel-independent), so that convolution is Cin times the k x k box sum of ONE channel -- a sum of 0/1 values,
+// exact in fp32 in any order.  Per output pixel: S = Cin * box(mask), update_mask = clamp(S, 0, 1),
+// mask_ratio = (Cin*k*k / (S + 1e-8)) * update_mask.  mask == nullptr is the reference's "no mask" case (all ones).
+__global__ void __launch_bounds__(256) k_pconv_mask(const float *__restrict__ mask, int H, int W, int Cin, int ksize, int stride,
+                                                    int pad, int Ho, int Wo, float *__restrict__ ratio, float *__restrict__ um,
+                                                    long total) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ox = (int)(i % Wo);
+  long r = i / Wo;
+  const int oy = (int)(r % Ho);
+  const int n = (int)(r / Ho);
+  const float *m = mask ? mask + (long)n * H * W : nullptr;
+  float box = 0.f;
+  for (int dy = 0; dy < ksize; ++dy) {
+    const int iy = oy * stride - pad + dy;
+    if (iy < 0 || iy >= H) continue;
+    for (int dx = 0; dx < ksize; ++dx) {
+      const int ix = ox * stride - pad + dx;
+      if (ix < 0 || ix >= W) continue;
+      box += m ? m[(long)iy * W + ix] : 1.f;
+    }
+  }
+  const float S = __fmul_rn(box, (float)Cin);
+  const float u = fminf(fmaxf(S, 0.f), 1.f);
+  // `self.slide_winsize / (self.update_mask + 1e-8)` is int / Tensor, which torch evaluates as reciprocal(tensor) * int
+  ratio[i] = __fmul_rn(__fmul_rn(__frcp_rn(__fadd_rn(S, 1e-8f)), (float)(Cin * ksize * ksize)), u);
+  um[i] = u;
 }
 
 // ---- host ------------------------------------------------------------------------------------------------------
@@ -860,8 +915,12 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
     p.out[o].ptr = a->out[o].ptr;
     p.out[o].stride = a->out[o].pixel_stride;
     p.out[o].slope = a->out[o].slope;
+    p.out[o].mul = a->out[o].mul;
     p.out[o].round_tf32 = a->out[o].round_tf32;
   }
+  KB_REQUIRE((a->pc_ratio == nullptr) == (a->pc_um == nullptr), "kb_conv2d: pc_ratio and pc_um come together");
+  p.pc_ratio = a->pc_ratio;
+  p.pc_um = a->pc_um;
   int rc = raise_smem_limit();
   if (rc) return rc;
   CUtensorMap map_a, map_b;
@@ -925,7 +984,7 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
 }
 
 int kb_upsample2x_prelu(const float *x, long x_stride, int N, int H, int W, int C, const float *slope, float *y, long y_stride,
-                        int Ho, int Wo, int round_tf32, kb_stream_t stream) {
+                        int Ho, int Wo, int round_tf32, const float *mul, kb_stream_t stream) {
   KB_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0 && Ho <= 2 * H && Wo <= 2 * W,
              "kb_upsample2x_prelu: bad arguments");
   KB_REQUIRE(x_stride % 4 == 0 && y_stride % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0,
@@ -933,7 +992,7 @@ int kb_upsample2x_prelu(const float *x, long x_stride, int N, int H, int W, int 
   const int C4 = (C + 3) / 4;
   const long total = (long)N * Ho * Wo * C4;
   k_upsample2x_prelu<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, x_stride, H, W, C4, slope, C, y, y_stride, Ho, Wo,
-                                                                        round_tf32, total);
+                                                                        round_tf32, total, mul);
   count_launch();
   return check_launch("kb_upsample2x_prelu");
 }
@@ -980,6 +1039,19 @@ int kb_nhwc_to_nchw(const float *x, long x_stride, int N, int C, int H, int W, f
   k_nhwc_to_nchw<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, x_stride, C, HW, y, mul, add, total);
   count_launch();
   return check_launch("kb_nhwc_to_nchw");
+}
+
+int kb_pconv_mask(const float *mask, int N, int H, int W, int Cin, int ksize, int stride, int pad, float *ratio, float *update_mask,
+                  kb_stream_t stream) {
+  KB_REQUIRE(ratio && update_mask && N > 0 && H > 0 && W > 0 && Cin > 0 && ksize >= 1 && ksize <= 7 && stride >= 1 && pad >= 0,
+             "kb_pconv_mask: bad arguments");
+  const int Ho = (H + 2 * pad - ksize) / stride + 1, Wo = (W + 2 * pad - ksize) / stride + 1;
+  KB_REQUIRE(Ho > 0 && Wo > 0, "kb_pconv_mask: empty output");
+  const long total = (long)N * Ho * Wo;
+  k_pconv_mask<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(mask, H, W, Cin, ksize, stride, pad, Ho, Wo, ratio, update_mask,
+                                                                  total);
+  count_launch();
+  return check_launch("kb_pconv_mask");
 }
 
 }  // extern "C"

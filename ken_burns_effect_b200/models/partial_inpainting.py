@@ -5,6 +5,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..utils import convstack as cs
 from ..utils.partial_conv import PartialConv2d
 from .gridnet import grid_name
 from .pointcloud_inpainting import Inpaint as _DenseInpaint
@@ -99,8 +100,19 @@ class Inpaint(_DenseInpaint):
         if tensorData is None and tensorContext is not None:
             tensorData = torch.cat([tensorImage, tensorDisparity, tensorContext], 1)
         elif tensorData is None:
-            tensorContext = self.moduleContext(torch.cat([tensorImage, tensorDisparity], 1))
+            tensorContext = (self._context_b200(tensorImage, tensorDisparity) if tensorImage.is_cuda
+                             else self.moduleContext(torch.cat([tensorImage, tensorDisparity], 1)))
             tensorData = torch.cat([tensorImage, tensorDisparity, tensorContext], 1)
+
+        if tensorData.is_cuda:
+            img, disp, k0 = self._forward_b200(tensorData, tensorMasks)
+            img, disp = self.normalize_images_disp(img, disp, not_normed=False)
+            return {
+                'tensorExisting': k0,
+                'tensorExistingInput': tensorMasks,
+                'tensorImage': img.clamp(0.0, 1.0) if self.training == False else img,  # noqa: E712
+                'tensorDisparity': F.threshold(input=disp, threshold=0.0, value=0.0),
+            }
 
         m = self._modules
         R = len(self.FEATURES)
@@ -133,3 +145,96 @@ class Inpaint(_DenseInpaint):
             'tensorImage': img.clamp(0.0, 1.0) if self.training == False else img,  # noqa: E712
             'tensorDisparity': F.threshold(input=disp, threshold=0.0, value=0.0),
         }
+
+    # -- the same forward on libkb200 (NHWC activations, tcgen05 convolutions with the partial-conv renormalisation, the
+    #    next layer's PReLU and the consumer's mask folded into the epilogue; utils/convstack.py) --------------------------
+    # Every mask of this network has identical channels (it starts as tensorMasks.expand_as(data), :152, and every update
+    # is channel-independent), so masks travel as ONE channel [N,H,W]; kb_pconv_mask turns a mask into the per-pixel
+    # mask_ratio / update_mask of a layer exactly (sums of 0/1 values).
+    @staticmethod
+    def _pblock(block, x_in, m_in, make_outs, x_raw=None, extra_res=None, merge_mask=None, crop=None):
+        """One Basic / Downsample / Upsample chain of PartialConv2d layers.
+        x_in : conv1's input with the block's leading PReLU and mask already applied by its producer (Upsample: the RAW
+               coarse input -- up-sampling, PReLU and masking happen here, partial_inpainting.py:88-93);
+        m_in : the mask travelling with x_in, [N,H,W], or None (heads: called without a mask, :212-213);
+        merge_mask: mask of the other branch arriving at the same grid cell (skip merge: torch.min, :167);
+        make_outs(k) -> output specs of cs.conv2d for the cell mask k.  Returns (outputs, k)."""
+        if getattr(block, 'upsample_first', False):
+            m_in = (F.interpolate(m_in[:, None], scale_factor=2, mode='bilinear', align_corners=False)[:, 0] > 0.5).float().contiguous()
+            x_in = cs.upsample2x_prelu(x_in, block.p_relu_1.weight, mul=m_in)
+        c1, c2 = block.conv1, block.conv2
+        N, H, W, _ = x_in.shape
+        r1, u1 = cs.pconv_mask(m_in, (N, H, W), c1.in_channels, c1.kernel_size[0], c1.stride[0], c1.padding[0])
+        t, = cs.conv2d(x_in, cs.packed(c1), [(block.p_relu_2.weight, True, None)], partial=(r1, u1))
+        r2, u2 = cs.pconv_mask(u1, tuple(u1.shape), c2.in_channels, c2.kernel_size[0], 1, c2.padding[0])
+        if crop is not None:
+            r2, u2 = r2[:, :crop[0], :crop[1]].contiguous(), u2[:, :crop[0], :crop[1]].contiguous()
+        k = u2 if merge_mask is None else torch.min(merge_mask, u2)
+        res = extra_res
+        if isinstance(block, Basic):
+            assert extra_res is None and x_raw is not None
+            sc = block.moduleShortcut
+            # the 1x1 shortcut is a PartialConv2d called without a mask (:47): ratio = Cin / (Cin + 1e-8) = 1, update_mask = 1
+            res = x_raw if sc is None else cs.conv2d(x_raw, cs.packed(sc), [(None, False, None)])[0]
+        return cs.conv2d(t, cs.packed(c2), make_outs(k), res=res, crop=crop, partial=(r2, u2)), k
+
+    def _forward_b200(self, tensorData, tensorMasks):
+        m = self._modules
+        F_ = self.FEATURES
+        R = len(F_)
+        N, C, H, W = tensorData.shape
+        m0 = tensorMasks[:, 0].contiguous()
+        x_raw = cs.to_nhwc(tensorData)
+        x_msk = cs.to_nhwc(tensorData * tensorMasks)                    # conv(input * mask), partial_conv.py:71
+
+        def pre(block):
+            return block.p_relu_1.weight if block.pre_relu else None
+
+        def cell_specs(r, c):
+            keys = []
+            if c < 3 or r > 0 or (r == 0 and c == 3):
+                keys.append(('raw', None))
+            if c < 3:
+                keys.append(('basic', pre(m[grid_name(r, c, r, c + 1)])))
+            if c in (0, 1) and r < R - 1:
+                keys.append(('down', pre(m[grid_name(r, c, r + 1, c)])))
+            return keys
+
+        def run(block, x_in, m_in, r, c, **kw):
+            keys = cell_specs(r, c)
+            outs, k = self._pblock(block, x_in, m_in,
+                                   lambda k: [(sl, sl is not None, None, k if sl is not None else None) for _, sl in keys], **kw)
+            cell = {name: t for (name, _), t in zip(keys, outs)}
+            cell['mask'] = k
+            return cell
+
+        def raw_only(block, x_in, m_in, **kw):
+            outs, k = self._pblock(block, x_in, m_in, lambda k: [(None, False, None)], **kw)
+            return outs[0], k
+
+        V = [None] * R
+        V[0] = run(self.moduleInput, x_msk, m0, 0, 0, x_raw=x_raw)
+        for r in range(1, R):                                            # column 0
+            V[r] = run(m[grid_name(r - 1, 0, r, 0)], V[r - 1]['down'], V[r - 1]['mask'], r, 0)
+        for r in range(R):                                               # column 1, top -> bottom
+            basic = m[grid_name(r, 0, r, 1)]
+            if r == 0:
+                V[0] = run(basic, V[0]['basic'], V[0]['mask'], 0, 1, x_raw=V[0]['raw'])
+            else:
+                t1, kb = raw_only(basic, V[r]['basic'], V[r]['mask'], x_raw=V[r]['raw'])
+                V[r] = run(m[grid_name(r - 1, 1, r, 1)], V[r - 1]['down'], V[r - 1]['mask'], r, 1, extra_res=t1, merge_mask=kb)
+        for c in (2, 3):                                                 # columns 2, 3, bottom -> top
+            for r in range(R - 1, -1, -1):
+                basic = m[grid_name(r, c - 1, r, c)]
+                if r == R - 1:
+                    V[r] = run(basic, V[r]['basic'], V[r]['mask'], r, c, x_raw=V[r]['raw'])
+                else:
+                    t1, kb = raw_only(basic, V[r]['basic'], V[r]['mask'], x_raw=V[r]['raw'])
+                    hw = (t1.size(1), t1.size(2))
+                    V[r] = run(m[grid_name(r + 1, c, r, c)], V[r + 1]['raw'], V[r + 1]['mask'], r, c, extra_res=t1,
+                               merge_mask=kb, crop=hw)
+        row0 = V[0]['raw']
+        img, _ = raw_only(self.moduleImage, row0, None, x_raw=row0)      # heads run without a mask (:212-213)
+        disp, _ = raw_only(self.moduleDisparity, row0, None, x_raw=row0)
+        k0 = V[0]['mask'][:, None].expand(N, F_[0], H, W)
+        return cs.to_nchw(img), cs.to_nchw(disp), k0

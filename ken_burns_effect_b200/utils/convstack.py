@@ -78,9 +78,11 @@ def packed(conv, bn=None):
     return cached[1]
 
 
-def conv2d(x, pc, outs, res=None, crop=None, tile_w=0, n_block=0, stages=0, algo=0):
-    """outs: list of (slope tensor | None, round_tf32 bool, destination view | None).  Returns the output views.
-    out_o = prelu_o(conv(x) + bias + res); crop=(Ho,Wo) keeps only the top-left part (reference: F.pad(..., -1))."""
+def conv2d(x, pc, outs, res=None, crop=None, tile_w=0, n_block=0, stages=0, algo=0, partial=None):
+    """outs: list of (slope tensor | None, round_tf32 bool, destination view | None[, mul mask [N,Ho,Wo] | None]).
+    Returns the output views.  out_o = prelu_o(pc(conv(x) + bias) + res) * mul_o; crop=(Ho,Wo) keeps only the top-left
+    part (reference: F.pad(..., -1)); partial=(ratio, update_mask), both [N,Ho,Wo] from pconv_mask(), turns the layer into
+    a PartialConv2d (utils/partial_conv.py:62-77)."""
     _check_act(x)
     N, H, W, Cin = x.shape
     if Cin != pc.Cin:
@@ -98,10 +100,24 @@ def conv2d(x, pc, outs, res=None, crop=None, tile_w=0, n_block=0, stages=0, algo
         if tuple(res.shape) != (N, Ho, Wo, pc.Cout):
             raise RuntimeError(f"conv2d: residual {tuple(res.shape)} does not match output {(N, Ho, Wo, pc.Cout)}")
         a.res, a.res_stride = res.data_ptr(), res.stride(2)
+    keep = []
+    if partial is not None:
+        ratio, um = partial
+        for t in (ratio, um):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (N, Ho, Wo)):
+                raise RuntimeError(f"conv2d: partial-conv maps must be contiguous fp32 {(N, Ho, Wo)}, got {tuple(t.shape)}")
+        a.pc_ratio, a.pc_um = ratio.data_ptr(), um.data_ptr()
+        keep += [ratio, um]
     a.n_out = len(outs)
     result = []
-    keep = []
-    for i, (slope, rnd, dst) in enumerate(outs):
+    for i, spec in enumerate(outs):
+        slope, rnd, dst = spec[:3]
+        mul = spec[3] if len(spec) > 3 else None
+        if mul is not None:
+            if not (mul.is_cuda and mul.dtype == torch.float32 and mul.is_contiguous() and tuple(mul.shape) == (N, Ho, Wo)):
+                raise RuntimeError(f"conv2d: mul mask must be contiguous fp32 {(N, Ho, Wo)}, got {tuple(mul.shape)}")
+            a.out[i].mul = mul.data_ptr()
+            keep.append(mul)
         if dst is None:
             dst = new_act(N, Ho, Wo, pc.Cout, x.device)
         _check_act(dst)
@@ -120,14 +136,31 @@ def conv2d(x, pc, outs, res=None, crop=None, tile_w=0, n_block=0, stages=0, algo
     return result
 
 
-def upsample2x_prelu(x, slope, out_hw=None, rnd=True):
+def upsample2x_prelu(x, slope, out_hw=None, rnd=True, mul=None):
+    """nn.Upsample(x2, bilinear) -> PReLU [-> * mul, a [N,Ho,Wo] mask] on an NHWC activation."""
     _check_act(x)
     N, H, W, C = x.shape
     Ho, Wo = (2 * H, 2 * W) if out_hw is None else out_hw
     y = new_act(N, Ho, Wo, C, x.device)
+    if mul is not None and not (mul.is_cuda and mul.dtype == torch.float32 and mul.is_contiguous() and tuple(mul.shape) == (N, Ho, Wo)):
+        raise RuntimeError(f"upsample2x_prelu: mul mask must be contiguous fp32 {(N, Ho, Wo)}")
     nat.check(nat.lib().kb_upsample2x_prelu(_ptr(x), x.stride(2), N, H, W, C, _ptr(slope.detach()) if slope is not None else None,
-                                            _ptr(y), y.stride(2), Ho, Wo, 1 if rnd else 0, _stream()), "kb_upsample2x_prelu")
+                                            _ptr(y), y.stride(2), Ho, Wo, 1 if rnd else 0, _ptr(mul), _stream()), "kb_upsample2x_prelu")
     return y
+
+
+def pconv_mask(mask, shape_nhw, Cin, ksize, stride, pad):
+    """Mask bookkeeping of a PartialConv2d(multi_channel=True) layer whose mask channels are identical
+    (utils/partial_conv.py:43-69): mask [N,H,W] of {0,1} or None (= no mask) -> (mask_ratio, update_mask), [N,Ho,Wo] each."""
+    N, H, W = shape_nhw
+    Ho, Wo = (H + 2 * pad - ksize) // stride + 1, (W + 2 * pad - ksize) // stride + 1
+    dev = mask.device if mask is not None else torch.device('cuda', torch.cuda.current_device())
+    if mask is not None and not (mask.is_cuda and mask.dtype == torch.float32 and mask.is_contiguous() and tuple(mask.shape) == (N, H, W)):
+        raise RuntimeError(f"pconv_mask: mask must be contiguous fp32 {(N, H, W)}, got {tuple(mask.shape)}")
+    ratio = torch.empty(N, Ho, Wo, device=dev, dtype=torch.float32)
+    um = torch.empty(N, Ho, Wo, device=dev, dtype=torch.float32)
+    nat.check(nat.lib().kb_pconv_mask(_ptr(mask), N, H, W, Cin, ksize, stride, pad, _ptr(ratio), _ptr(um), _stream()), "kb_pconv_mask")
+    return ratio, um
 
 
 def prelu(x, slope, rnd=True, dst=None):

@@ -122,6 +122,39 @@ def test_elementwise_companions():
     assert torch.allclose(cs.to_nchw(cs.to_nhwc(x, sub=0.5, mul=2.0), mul=0.5, add=0.5), x, atol=1e-6)
 
 
+def test_partial_conv_layer_vs_torch_module():
+    """kb_pconv_mask + the partial-conv epilogue of kb_conv2d against the PartialConv2d mirror (torch ops; itself checked
+    against the reference's utils/partial_conv.py in tests/test_models_cpu.py) on a mask with identical channels."""
+    from ken_burns_effect_b200.utils.partial_conv import PartialConv2d
+    g = torch.Generator().manual_seed(21)
+    for (cin, cout, k, stride) in [(32, 48, 3, 1), (20, 32, 3, 2), (68, 32, 1, 1)]:
+        # the torch module runs on the CPU: its direct convolution sums the 0/1 mask exactly, whereas cuDNN may pick an
+        # algorithm (Winograd / FFT) that turns an exact 0 into 1e-7 and with it update_mask into a non-binary value
+        pc = PartialConv2d(cin, cout, kernel_size=k, stride=stride, padding=k // 2, multi_channel=True, return_mask=True)
+        x = torch.randn(2, cin, 37, 52, generator=g)
+        m1 = (torch.rand(2, 1, 37, 52, generator=g) > 0.4).float()
+        m1[:, :, 10:20, 5:30] = 0                       # a hole wider than the filter: update_mask = 0 inside
+        ref, ref_um = pc(x, mask_in=m1.expand_as(x).contiguous())
+        ref_ratio = pc.mask_ratio.clone()
+        # no mask: the zero-padded border is still renormalised (x1.5 / x2.25 for 3x3).  A fresh module: a PartialConv2d
+        # called without a mask REUSES the ratio of its previous call when the shape is unchanged (partial_conv.py:45)
+        pc_nomask = PartialConv2d(cin, cout, kernel_size=k, stride=stride, padding=k // 2, multi_channel=True, return_mask=True)
+        pc_nomask.load_state_dict(pc.state_dict())
+        ref2, _ = pc_nomask(x)
+        pcg = PartialConv2d(cin, cout, kernel_size=k, stride=stride, padding=k // 2, multi_channel=True, return_mask=True).cuda()
+        pcg.load_state_dict(pc.state_dict())
+        ratio, um = cs.pconv_mask(m1[:, 0].contiguous().cuda(), (2, 37, 52), cin, k, stride, k // 2)
+        assert torch.equal(um.cpu(), ref_um[:, 0])             # bit-exact mask and ratio
+        assert torch.equal(ratio.cpu(), ref_ratio[:, 0])
+        got, = cs.conv2d(nhwc((x * m1).cuda()), cs.packed(pcg), [(None, False, None)], partial=(ratio, um))
+        got = got.permute(0, 3, 1, 2).cpu()
+        assert rel(got, ref) < 2e-3
+        assert float(got[ref_um == 0].abs().max()) == 0.0
+        r2, u2 = cs.pconv_mask(None, (2, 37, 52), cin, k, stride, k // 2)
+        got2, = cs.conv2d(nhwc(x.cuda()), cs.packed(pcg), [(None, False, None)], partial=(r2, u2))
+        assert rel(got2.permute(0, 3, 1, 2).cpu(), ref2) < 2e-3
+
+
 def T(k):
     return torch.from_numpy(G[k]).cuda()
 
@@ -144,3 +177,9 @@ def test_networks_vs_reference_goldens():
     o = net(mask, tensorImage=T("ref_img") * mask, tensorDisparity=T("inp_disp") * mask)
     for k in ("tensorExisting", "tensorImage", "tensorDisparity"):
         assert rel(o[k], T(f"inpaint_{k}")) < 1e-2, k
+    from ken_burns_effect_b200.models.partial_inpainting import Inpaint as PartialInpaint
+    net = kb_helpers.deterministic_state(PartialInpaint().eval()).cuda()
+    o = net(mask, tensorImage=T("ref_img") * mask, tensorDisparity=T("inp_disp") * mask)
+    assert torch.equal(o["tensorExisting"], T("partial_tensorExisting"))          # masks are exact
+    for k in ("tensorImage", "tensorDisparity"):
+        assert rel(o[k], T(f"partial_{k}")) < 1e-2, k

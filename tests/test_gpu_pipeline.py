@@ -46,12 +46,14 @@ def test_pipeline_dolly_runs_and_matches_frame_oracle():
             f"frame {i}: max {d.max()}, differing bytes {(d > 0).mean():.2e}, >1: {(d > 1).sum()}"
 
 
-def test_pipeline_with_inpainting_grows_the_cloud():
+@pytest.mark.parametrize("partial", [False, True])
+def test_pipeline_with_inpainting_grows_the_cloud(partial):
+    """Full KBE with the two inpainting passes (dense Inpaint, and PartialInpaint = kbe.py --partial-conv)."""
     torch.manual_seed(1)
     W, H = 384, 320
     img, _ = synthetic.synthetic_scene(W, H, seed=6)
     t = torch.from_numpy(img).permute(2, 0, 1).float().div(255).view(1, 3, H, W)
-    pipe = Pipeline(model_paths=None, dolly=False, frames=3)
+    pipe = Pipeline(model_paths=None, partial_inpainting=partial, dolly=False, frames=3)
     frames = pipe(t, synthetic.default_zoom(W, H))
     oc = pipe.objectCommon
     n = oc['tensorInpaPoints'].shape[-1]
