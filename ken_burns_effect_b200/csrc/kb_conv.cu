@@ -93,6 +93,34 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with each shared-memory descriptor given as its two 32-bit halves: only the low word (start address) changes from
+// one MMA to the next, so a step costs one 32-bit add instead of 64-bit arithmetic.
+__device__ __forceinline__ void umma_tf32_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// One lane of a converged warp.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // mbarrier arrive when every MMA issued so far by this thread has finished reading smem / writing TMEM.
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -244,7 +272,12 @@ __device__ __forceinline__ void epilogue_rows(const ConvKernelParams &p, const E
   for (int c0 = 16 * half; c0 < p.Npad; c0 += 32) {
     if (n0 + c0 >= p.Cout4) break;           // warp-uniform
     uint32_t raw[16];
-    tmem_ld16_issue(taddr + (uint32_t)c0, raw);
+    if (p.debug & 8) {   // experiment: no TMEM reads
+#pragma unroll
+      for (int i = 0; i < 16; ++i) raw[i] = 0;
+    } else {
+      tmem_ld16_issue(taddr + (uint32_t)c0, raw);
+    }
     float4 rnext[4];
     const bool more = (c0 + 32 < p.Npad) && (n0 + c0 + 32 < p.Cout4);
     if (more) epi_load_res(p, px, n0 + c0 + 32, rnext);
@@ -408,6 +441,38 @@ __global__ void __launch_bounds__(kConvThreads) k_conv_tf32(const __grid_constan
 // epilogue of tile i overlaps the MMAs of tile i+1, and filters small enough stay resident in shared memory.
 constexpr int kHaloTileW = 8, kHaloTileH = 16;
 
+// Work item w = ((img * tiles_y + ty) * tiles_x + tx) * n_blocks + nb, visited as w = blockIdx.x, += gridDim.x, ...
+// The coordinates are carried along as mixed-radix digits: the 64-bit divisions of a direct decomposition cost each of
+// the eight epilogue warps several hundred instructions per tile, which made THEM the bottleneck of small tiles.
+struct TileIter {
+  int nb, tx, ty, img;
+  int d_nb, d_tx, d_ty, d_img;
+  int left;
+  __device__ __forceinline__ void init(const ConvKernelParams &p) {
+    long w = blockIdx.x, step = gridDim.x;
+    left = w < p.work_items ? (int)((p.work_items - w + step - 1) / step) : 0;
+    nb = (int)(w % p.n_blocks); w /= p.n_blocks;
+    tx = (int)(w % p.tiles_x); w /= p.tiles_x;
+    ty = (int)(w % p.tiles_y); img = (int)(w / p.tiles_y);
+    d_nb = (int)(step % p.n_blocks); step /= p.n_blocks;
+    d_tx = (int)(step % p.tiles_x); step /= p.tiles_x;
+    d_ty = (int)(step % p.tiles_y); d_img = (int)(step / p.tiles_y);
+  }
+  __device__ __forceinline__ void next(const ConvKernelParams &p) {
+    --left;
+    nb += d_nb;
+    int c = nb >= p.n_blocks;
+    nb -= c ? p.n_blocks : 0;
+    tx += d_tx + c;
+    c = tx >= p.tiles_x;
+    tx -= c ? p.tiles_x : 0;
+    ty += d_ty + c;
+    c = ty >= p.tiles_y;
+    ty -= c ? p.tiles_y : 0;
+    img += d_img + c;
+  }
+};
+
 // Measured on B200 (tools/probe_halo.py, profiles/probe_halo_r01.jsonl): the tensor core applies the 128-byte swizzle XOR
 // to the ABSOLUTE shared-memory address bits [7,10), exactly like TMA does when it writes the tile.  A descriptor may
 // therefore start at any 128-byte row of a TMA-written tile and use any multiple of 128 bytes as its stride between
@@ -460,18 +525,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
       // ===== TMA producer =====
       uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
       bool first = true;
-      for (long w = blockIdx.x; w < p.work_items; w += gridDim.x) {
-        const int nb = (int)(w % p.n_blocks);
-        long t = w / p.n_blocks;
-        const int tx = (int)(t % p.tiles_x);
-        t /= p.tiles_x;
-        const int ty = (int)(t % p.tiles_y);
-        const int img = (int)(t / p.tiles_y);
-        const int cx = tx * kHaloTileW - p.pad, cy = ty * kHaloTileH - p.pad, cn = nb * p.Npad;
+      TileIter it;
+      for (it.init(p); it.left > 0; it.next(p)) {
+        const int img = it.img;
+        const int cx = it.tx * kHaloTileW - p.pad, cy = it.ty * kHaloTileH - p.pad, cn = it.nb * p.Npad;
         for (int ck = 0; ck < p.chunks; ++ck) {
           mbar_wait(a_empty + sa, pha ^ 1u);
-          mbar_expect_tx(a_full + sa, (uint32_t)kBoxBytes);
-          tma_load_4d(&map_a, a_full + sa, smem_a + (size_t)sa * kAStage, ck * kChunk, cx, cy, img);
+          if (p.debug & 4) {   // experiment: no activation loads, barriers only
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(a_full + sa)) : "memory");
+          } else {
+            mbar_expect_tx(a_full + sa, (uint32_t)kBoxBytes);
+            tma_load_4d(&map_a, a_full + sa, smem_a + (size_t)sa * kAStage, ck * kChunk, cx, cy, img);
+          }
           if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; }
           if (!p.resident || first) {
             int j = ck;                                   // packed weights: panel (tap, ck) at index tap*chunks + ck
@@ -487,49 +552,55 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      const uint64_t tmpl_a = umma_desc_sw128_sbo(0, kPitch * kChunk * 4), tmpl_b = umma_desc_sw128(0);
-      const uint32_t a_base_lo = smem_u32(smem_a) >> 4, b_base_lo = smem_u32(smem_b) >> 4, b_step_lo = (uint32_t)b_bytes >> 4;
-      uint32_t sa = 0, pha = 0, a_lo = a_base_lo;
-      uint32_t sb = 0, phb = 0, b_lo = b_base_lo;
-      uint32_t as = 0, phacc = 0;
-      bool first = true;
-      for (long w = blockIdx.x; w < p.work_items; w += gridDim.x) {
-        mbar_wait(acc_empty + as, phacc ^ 1u);
+    // ===== MMA issuer =====
+    // The WHOLE warp runs this loop and one elected lane issues the tcgen05 instructions.  With the loop inside
+    // `if (lane == 0)` the compiler keeps the ring state in per-thread registers and moves every descriptor into uniform
+    // registers one MMA at a time: ncu showed ~17 dependent instructions (~128 cycles) per MMA on the issuing thread, i.e.
+    // the tensor pipe (16-64 cycles per MMA) waited for its own issue loop and every other role waited for the tensor pipe.
+    const bool leader = elect_one();
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    const uint64_t tmpl_a = umma_desc_sw128_sbo(0, kPitch * kChunk * 4), tmpl_b = umma_desc_sw128(0);
+    const uint32_t a_hi = (uint32_t)(tmpl_a >> 32), b_hi = (uint32_t)(tmpl_b >> 32);
+    const uint32_t a_tl = (uint32_t)tmpl_a, b_tl = (uint32_t)tmpl_b;          // low words without the address field
+    const uint32_t a_base_lo = smem_u32(smem_a) >> 4, b_base_lo = smem_u32(smem_b) >> 4, b_step_lo = (uint32_t)b_bytes >> 4;
+    uint32_t sa = 0, pha = 0, a_lo = a_base_lo;
+    uint32_t sb = 0, phb = 0, b_lo = b_base_lo;
+    uint32_t as = 0, phacc = 0;
+    bool first = true;
+    const int n_items = blockIdx.x < p.work_items ? (int)((p.work_items - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    for (int item = 0; item < n_items; ++item) {
+      mbar_wait(acc_empty + as, phacc ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * (uint32_t)p.Npad;
+      if (p.resident) { sb = 0; b_lo = b_base_lo; }     // resident panels: slot index = ck*taps + tap, loaded once
+      for (int ck = 0; ck < p.chunks; ++ck) {
+        mbar_wait(a_full + sa, pha);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * (uint32_t)p.Npad;
-        if (p.resident) { sb = 0; b_lo = b_base_lo; }     // resident panels: slot index = ck*taps + tap, loaded once
-        for (int ck = 0; ck < p.chunks; ++ck) {
-          mbar_wait(a_full + sa, pha);
-          tc_fence_after();
 #pragma unroll
-          for (int tap = 0; tap < kTaps; ++tap) {
-            if (!p.resident || first) {
-              mbar_wait(b_full + sb, phb);
-              tc_fence_after();
-            }
-            const uint32_t a_off = (uint32_t)(((tap / KS) * kPitch + (tap % KS)) * kChunk * 4) >> 4;   // compile-time
-            if (!(p.debug & 2)) {
-#pragma unroll
-              for (int k = 0; k < kChunk / 8; ++k)
-                umma_tf32(d_tmem, tmpl_a | (uint64_t)(a_lo + a_off + 2 * k), tmpl_b | (uint64_t)(b_lo + 2 * k), idesc,
-                          (uint32_t)((ck != 0) | (tap != 0) | (k != 0)));
-            }
-            if (!p.resident) umma_commit(b_empty + sb);
-            b_lo += b_step_lo;
-            if (++sb == (uint32_t)p.b_stages) { sb = 0; phb ^= (p.resident ? 0u : 1u); b_lo = b_base_lo; }
+        for (int tap = 0; tap < kTaps; ++tap) {
+          if (!p.resident || first) {
+            mbar_wait(b_full + sb, phb);
+            tc_fence_after();
           }
-          umma_commit(a_empty + sa);
-          a_lo += kAStage >> 4;
-          if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; a_lo = a_base_lo; }
+          const uint32_t a_off = (uint32_t)(((tap / KS) * kPitch + (tap % KS)) * kChunk * 4) >> 4;   // compile-time
+          if (leader && !(p.debug & 2)) {
+#pragma unroll
+            for (int k = 0; k < kChunk / 8; ++k)
+              umma_tf32_lh(d_tmem, a_tl | ((a_lo + a_off + 2 * k) & 0x3FFF), a_hi, b_tl | ((b_lo + 2 * k) & 0x3FFF), b_hi, idesc,
+                           (uint32_t)((ck != 0) | (tap != 0) | (k != 0)));
+          }
+          if (!p.resident && leader) umma_commit(b_empty + sb);
+          b_lo += b_step_lo;
+          if (++sb == (uint32_t)p.b_stages) { sb = 0; phb ^= (p.resident ? 0u : 1u); b_lo = b_base_lo; }
         }
-        umma_commit(acc_full + as);
-        as ^= 1u;
-        if (as == 0) phacc ^= 1u;
-        first = false;
+        if (leader) umma_commit(a_empty + sa);
+        a_lo += kAStage >> 4;
+        if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; a_lo = a_base_lo; }
       }
+      if (leader) umma_commit(acc_full + as);
+      as ^= 1u;
+      if (as == 0) phacc ^= 1u;
+      first = false;
     }
   } else {
     // ===== epilogue warps =====
@@ -538,19 +609,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
     const int py = m / kHaloTileW, px = m - py * kHaloTileW;
     const EpiSmem es = epi_stage(p, epi_tab, p.cpad, threadIdx.x - 64);
     uint32_t as = 0, phacc = 0;
-    for (long w = blockIdx.x; w < p.work_items; w += gridDim.x) {
-      const int nb = (int)(w % p.n_blocks);
-      long t = w / p.n_blocks;
-      const int tx = (int)(t % p.tiles_x);
-      t /= p.tiles_x;
-      const int ty = (int)(t % p.tiles_y);
-      const int img = (int)(t / p.tiles_y);
-      const EpiPixel ep = epi_pixel(p, img, ty * kHaloTileH + py, tx * kHaloTileW + px);
+    TileIter it;
+    for (it.init(p); it.left > 0; it.next(p)) {
+      const int n0 = it.nb * p.Npad;
+      const EpiPixel ep = epi_pixel(p, it.img, it.ty * kHaloTileH + py, it.tx * kHaloTileW + px);
       float4 rr[4];
-      epi_load_res(p, ep, nb * p.Npad + 16 * half, rr);        // in flight while the MMAs of this tile finish
+      epi_load_res(p, ep, n0 + 16 * half, rr);                 // in flight while the MMAs of this tile finish
       mbar_wait(acc_full + as, phacc);
       tc_fence_after();
-      epilogue_rows(p, es, ep, tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.Npad, nb * p.Npad, half, rr);
+      epilogue_rows(p, es, ep, tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.Npad, n0, half, rr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
@@ -780,6 +847,8 @@ int kb_conv_pack_weights(const float *w_oihw, int Cout, int Cin, int ksize, cons
   return check_launch("kb_conv_pack_weights");
 }
 
+
+
 static int env_int(const char *name, int dflt) {
   const char *v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -807,9 +876,12 @@ static int make_act_map(EncodeTiledFn enc, const kb_conv_args *a, int box_w, int
                            (cuuint64_t)a->x_stride * 4 * a->W * a->H};
   cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  static const int promo = env_int("KB_TMA_PROMO", 2);
+  const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                    : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                    : promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(a->x), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("kb_conv2d: cuTensorMapEncodeTiled(activations) failed with CUresult %d", (int)r);
     return KB_EINVAL;

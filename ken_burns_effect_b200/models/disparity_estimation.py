@@ -39,7 +39,7 @@ class Semantics(nn.Module):
         mean = x.new_tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
         std = x.new_tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
         x = (x - mean) / std
-        return self._vgg_b200(x) if x.is_cuda else self.moduleVgg(x)
+        return cs.graphed(self, 'vgg', self._vgg_b200, x.contiguous()) if x.is_cuda else self.moduleVgg(x)
 
     def _vgg_b200(self, x):
         """The VGG19-bn trunk on libkb200 convolutions: eval-mode BatchNorm folded into filter and bias, ReLU in the
@@ -79,7 +79,7 @@ class Disparity(nn.Module):
 
     def forward(self, tensorImage, tensorSemantics):
         if tensorImage.is_cuda:
-            return self._forward_b200(tensorImage, tensorSemantics)
+            return cs.graphed(self, 'forward', self._forward_b200, tensorImage.contiguous(), tensorSemantics.contiguous())
         m = self._modules
         rows = [self.moduleImage(tensorImage)]
         for r in range(1, len(self.FEATURES)):

@@ -27,7 +27,7 @@ class Refine(nn.Module):
         img = (tensorImage - mean[0]) / (std[0] + 0.0000001)
         disp = (tensorDisparity - mean[1]) / (std[1] + 0.0000001)
         if img.is_cuda:
-            return self._forward_b200(img, disp) * (std[1] + 0.0000001) + mean[1]
+            return cs.graphed(self, 'forward', self._forward_b200, img.contiguous(), disp.contiguous()) * (std[1] + 0.0000001) + mean[1]
         one = self.moduleImageOne(img)
         two = self.moduleImageTwo(one)
         thr = self.moduleImageThr(two)

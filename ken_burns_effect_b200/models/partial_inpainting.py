@@ -100,12 +100,13 @@ class Inpaint(_DenseInpaint):
         if tensorData is None and tensorContext is not None:
             tensorData = torch.cat([tensorImage, tensorDisparity, tensorContext], 1)
         elif tensorData is None:
-            tensorContext = (self._context_b200(tensorImage, tensorDisparity) if tensorImage.is_cuda
+            tensorContext = (self._context(tensorImage, tensorDisparity) if tensorImage.is_cuda
                              else self.moduleContext(torch.cat([tensorImage, tensorDisparity], 1)))
             tensorData = torch.cat([tensorImage, tensorDisparity, tensorContext], 1)
 
         if tensorData.is_cuda:
-            img, disp, k0 = self._forward_b200(tensorData, tensorMasks)
+            img, disp, k0 = cs.graphed(self, 'grid', self._forward_b200, tensorData.contiguous(), tensorMasks.contiguous())
+            k0 = k0[:, None].expand(tensorData.shape[0], self.FEATURES[0], tensorData.shape[2], tensorData.shape[3])
             img, disp = self.normalize_images_disp(img, disp, not_normed=False)
             return {
                 'tensorExisting': k0,
@@ -236,5 +237,4 @@ class Inpaint(_DenseInpaint):
         row0 = V[0]['raw']
         img, _ = raw_only(self.moduleImage, row0, None, x_raw=row0)      # heads run without a mask (:212-213)
         disp, _ = raw_only(self.moduleDisparity, row0, None, x_raw=row0)
-        k0 = V[0]['mask'][:, None].expand(N, F_[0], H, W)
-        return cs.to_nchw(img), cs.to_nchw(disp), k0
+        return cs.to_nchw(img), cs.to_nchw(disp), V[0]['mask']

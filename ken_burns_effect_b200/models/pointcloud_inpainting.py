@@ -54,12 +54,12 @@ class Inpaint(nn.Module):
         if tensorData is None and tensorContext is not None:
             tensorData = torch.cat([tensorImage, tensorDisparity, tensorContext], 1)
         elif tensorData is None:
-            tensorContext = (self._context_b200(tensorImage, tensorDisparity) if tensorImage.is_cuda
+            tensorContext = (self._context(tensorImage, tensorDisparity) if tensorImage.is_cuda
                              else self.moduleContext(torch.cat([tensorImage, tensorDisparity], 1)))
             tensorData = torch.cat([tensorImage, tensorDisparity, tensorContext], 1)
 
         if tensorData.is_cuda:
-            img, disp = self._grid_b200(tensorData, tensorMasks)
+            img, disp = cs.graphed(self, 'grid', self._grid_b200, tensorData.contiguous(), tensorMasks.contiguous())
         else:
             rows = grid_forward(self, self._column0(tensorData, tensorMasks))
             img, disp = self.moduleImage(rows[0]), self.moduleDisparity(rows[0])
@@ -80,6 +80,9 @@ class Inpaint(nn.Module):
         row0 = cs.grid_forward_nhwc(self, self.FEATURES, lambda outs: cs.run_block(self.moduleInput, x, outs, x_raw=x))
         return cs.to_nchw(cs.head_nhwc(self.moduleImage, row0)), cs.to_nchw(cs.head_nhwc(self.moduleDisparity, row0))
 
+    def _context(self, img, disp):
+        return cs.graphed(self, 'context', self._context_b200, img.contiguous(), disp.contiguous())
+
     def _context_b200(self, img, disp):
         """moduleContext (:89-94): conv(4->64) PReLU conv(64->64) PReLU, returned NCHW for the 68-channel splat."""
         x = cs.to_nhwc(torch.cat([img, disp], 1))
@@ -97,7 +100,7 @@ class Inpaint(nn.Module):
         valid = (kb.spatial_filter(tensorDisparity / tensorDisparity.max(), 'laplacian').abs() < 0.03).float()
         points = kb.depth_to_points(depth * valid, dblFocal).view(1, 3, -1)
         img, disp = self.normalize_images_disp(tensorImage, tensorDisparity, not_normed=True)
-        context = self._context_b200(img, disp) if img.is_cuda else self.moduleContext(torch.cat([img, disp], 1))
+        context = self._context(img, disp) if img.is_cuda else self.moduleContext(torch.cat([img, disp], 1))
         render, existing = kb.render_pointcloud(points + tensorShift, torch.cat([img, disp, context], 1).view(1, 68, -1),
                                                 objectCommon['intWidth'], objectCommon['intHeight'], dblFocal,
                                                 objectCommon['dblBaseline'])

@@ -340,15 +340,40 @@ def crop_size(objectSettings):
     return max(f['intCropWidth'], t['intCropWidth']), max(f['intCropHeight'], t['intCropHeight'])
 
 
+_PINNED = {}      # shape -> [pinned uint8 tensors]; cudaHostAlloc of 354 MB costs more than rendering 150 frames
+_RENDERERS = {}   # (device, H, W, crop, baseline) -> FrameRenderer (workspace, staging buffers, copy stream)
+
+
+def pinned_frames(shape):
+    """A pinned uint8 host buffer of `shape`, recycled from earlier calls once nobody else holds it (numpy views made
+    with .numpy() keep their tensor alive, so frames still in use by the caller are never overwritten)."""
+    import sys
+    pool = _PINNED.setdefault(tuple(shape), [])
+    for t in pool:
+        if sys.getrefcount(t) <= 3:          # the pool's list, the loop variable, getrefcount's argument
+            return t
+    t = torch.empty(*shape, dtype=torch.uint8).pin_memory()
+    if len(pool) < 4:
+        pool.append(t)
+    return t
+
+
 def render_poses(objectSettings, objectCommon, poses, to_host=True):
     """Stage B, utils/common.py:222-260, for the given poses of the path -> uint8 [len(poses),H,W,3]
     (pinned host memory when to_host, else on the cloud's device)."""
     crop_w, crop_h = crop_size(objectSettings)
-    renderer = FrameRenderer(objectCommon['tensorInpaPoints'], objectCommon['tensorInpaImage'],
-                             objectCommon['tensorInpaDepth'], objectCommon['intWidth'], objectCommon['intHeight'],
-                             objectCommon['dblBaseline'], crop_w, crop_h)
+    pts = objectCommon['tensorInpaPoints']
+    key = (pts.device, int(objectCommon['intHeight']), int(objectCommon['intWidth']), crop_w, crop_h, float(objectCommon['dblBaseline']))
+    renderer = _RENDERERS.get(key)
+    if renderer is None:
+        _RENDERERS.clear()                    # one geometry at a time: the workspace is ~0.45 GB at 1024x768
+        renderer = _RENDERERS[key] = FrameRenderer(pts, objectCommon['tensorInpaImage'], objectCommon['tensorInpaDepth'],
+                                                   objectCommon['intWidth'], objectCommon['intHeight'],
+                                                   objectCommon['dblBaseline'], crop_w, crop_h)
+    else:
+        renderer.set_cloud(pts, objectCommon['tensorInpaImage'], objectCommon['tensorInpaDepth'])
     if to_host:
-        out = torch.empty(len(poses), renderer.H, renderer.W, 3, dtype=torch.uint8).pin_memory()
+        out = pinned_frames((len(poses), renderer.H, renderer.W, 3))
     else:
         out = torch.empty(len(poses), renderer.H, renderer.W, 3, dtype=torch.uint8, device=renderer.device)
     if len(poses):

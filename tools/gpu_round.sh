@@ -7,7 +7,7 @@ python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/pytest_gpu_$TAG
 python tools/diag_degrid_race.py > gpurun_out/diag_$TAG.jsonl 2> gpurun_out/diag_$TAG.err; tail -2 gpurun_out/diag_$TAG.err
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; tail -3 gpurun_out/bench_$TAG.err; cat gpurun_out/bench_$TAG.json
 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 200 --csv --log-file gpurun_out/launches_$TAG.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_$TAG.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-full-pipeline > gpurun_out/ncu_bench_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'kf_accum|kf_fill|kf_splat_min|kf_degrid|kf_resolve|kf_crop_resize' -s 12 -c 6 \
-    -o gpurun_out/prof_$TAG -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_$TAG.log 2>&1
+    -o gpurun_out/prof_$TAG -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-full-pipeline > gpurun_out/ncu_full_$TAG.log 2>&1
 ls -la gpurun_out | tail -12
