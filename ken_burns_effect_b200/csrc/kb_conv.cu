@@ -371,47 +371,49 @@ __global__ void __launch_bounds__(kConvThreads) k_conv_tf32(const __grid_constan
   const int taps = p.ksize * p.ksize;
   const int J = taps * p.chunks;
 
-  // The single-thread issue loops below run on the uniform datapath, where every dependent instruction costs ~10
-  // cycles: ring indices are counters with explicit wrap-around (no division / modulo per step) and descriptors are
-  // a constant template plus a 14-bit address field.
+  // Producer and MMA issuer are whole warps running their loops convergently, with one elected lane issuing the TMA /
+  // tcgen05 instructions: ring state and descriptors then live in uniform registers (see k_conv_halo_tf32).
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      uint32_t s = 0, ph = 0;
-      int j = 0;
-      const int cx = x0 * p.stride - p.pad, cy = y0 * p.stride - p.pad;
-      for (int r = 0; r < p.ksize; ++r)
-        for (int q = 0; q < p.ksize; ++q)
-          for (int ck = 0; ck < p.chunks; ++ck, ++j) {
-            mbar_wait(empty + s, ph ^ 1u);
-            uint8_t *a_dst = smem + (size_t)s * stage_bytes;
+    // ===== TMA producer =====
+    const bool leader = elect_one();
+    uint32_t s = 0, ph = 0;
+    int j = 0;
+    const int cx = x0 * p.stride - p.pad, cy = y0 * p.stride - p.pad;
+    for (int r = 0; r < p.ksize; ++r)
+      for (int q = 0; q < p.ksize; ++q)
+        for (int ck = 0; ck < p.chunks; ++ck, ++j) {
+          mbar_wait(empty + s, ph ^ 1u);
+          uint8_t *a_dst = smem + (size_t)s * stage_bytes;
+          if (leader) {
             mbar_expect_tx(full + s, (uint32_t)stage_bytes);
             tma_load_4d(&map_a, full + s, a_dst, ck * kChunk, cx + q, cy + r, img);
             tma_load_3d(&map_b, full + s, a_dst + kABytes, 0, n0, j);
-            if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
           }
-    }
+          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+        }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      const uint32_t idesc = (1u << 4) /* D fp32 */ | (2u << 7) /* A tf32 */ | (2u << 10) /* B tf32 */ |
-                             ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      const uint64_t tmpl = umma_desc_sw128(0);
-      const uint32_t base_lo = smem_u32(smem) >> 4, stage_lo = (uint32_t)stage_bytes >> 4;
-      uint32_t s = 0, ph = 0, lo = base_lo;
-      for (int j = 0; j < J; ++j) {
-        mbar_wait(full + s, ph);
-        tc_fence_after();
-        const uint64_t da = tmpl | lo, db = tmpl | (lo + (kABytes >> 4));
+    // ===== MMA issuer =====
+    const bool leader = elect_one();
+    const uint32_t idesc = (1u << 4) /* D fp32 */ | (2u << 7) /* A tf32 */ | (2u << 10) /* B tf32 */ |
+                           ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    const uint64_t tmpl = umma_desc_sw128(0);
+    const uint32_t d_hi = (uint32_t)(tmpl >> 32), d_tl = (uint32_t)tmpl;
+    const uint32_t base_lo = smem_u32(smem) >> 4, stage_lo = (uint32_t)stage_bytes >> 4;
+    uint32_t s = 0, ph = 0, lo = base_lo;
+    for (int j = 0; j < J; ++j) {
+      mbar_wait(full + s, ph);
+      tc_fence_after();
+      if (leader) {
 #pragma unroll
         for (int k = 0; k < kChunk / 8; ++k)   // UMMA K = 8 tf32 = 32 bytes: advance the start address inside the swizzle row
-          umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (j | k) != 0);
+          umma_tf32_lh(tmem_base, d_tl | ((lo + 2 * k) & 0x3FFF), d_hi, d_tl | ((lo + (kABytes >> 4) + 2 * k) & 0x3FFF), d_hi, idesc,
+                       (uint32_t)((j | k) != 0));
         umma_commit(empty + s);                // slot reusable once these MMAs have read it
-        lo += stage_lo;
-        if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; lo = base_lo; }
       }
-      umma_commit(acc_full);                   // accumulator complete
+      lo += stage_lo;
+      if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; lo = base_lo; }
     }
+    if (leader) umma_commit(acc_full);         // accumulator complete
   } else {
     // ===== epilogue: warps 2..9; warp w may only touch TMEM lanes 32*(w%4) .. +31 =====
     const int q = warp & 3, half = (warp - 2) >> 2;
@@ -521,35 +523,38 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
-      bool first = true;
-      TileIter it;
-      for (it.init(p); it.left > 0; it.next(p)) {
-        const int img = it.img;
-        const int cx = it.tx * kHaloTileW - p.pad, cy = it.ty * kHaloTileH - p.pad, cn = it.nb * p.Npad;
-        for (int ck = 0; ck < p.chunks; ++ck) {
-          mbar_wait(a_empty + sa, pha ^ 1u);
+    // ===== TMA producer (whole warp, one elected lane issues) =====
+    const bool leader = elect_one();
+    uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
+    bool first = true;
+    TileIter it;
+    for (it.init(p); it.left > 0; it.next(p)) {
+      const int img = it.img;
+      const int cx = it.tx * kHaloTileW - p.pad, cy = it.ty * kHaloTileH - p.pad, cn = it.nb * p.Npad;
+      for (int ck = 0; ck < p.chunks; ++ck) {
+        mbar_wait(a_empty + sa, pha ^ 1u);
+        if (leader) {
           if (p.debug & 4) {   // experiment: no activation loads, barriers only
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(a_full + sa)) : "memory");
           } else {
             mbar_expect_tx(a_full + sa, (uint32_t)kBoxBytes);
             tma_load_4d(&map_a, a_full + sa, smem_a + (size_t)sa * kAStage, ck * kChunk, cx, cy, img);
           }
-          if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; }
-          if (!p.resident || first) {
-            int j = ck;                                   // packed weights: panel (tap, ck) at index tap*chunks + ck
-            for (int tap = 0; tap < kTaps; ++tap, j += p.chunks) {
-              mbar_wait(b_empty + sb, phb ^ 1u);
+        }
+        if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; }
+        if (!p.resident || first) {
+          int j = ck;                                   // packed weights: panel (tap, ck) at index tap*chunks + ck
+          for (int tap = 0; tap < kTaps; ++tap, j += p.chunks) {
+            mbar_wait(b_empty + sb, phb ^ 1u);
+            if (leader) {
               mbar_expect_tx(b_full + sb, (uint32_t)b_bytes);
               tma_load_3d(&map_b, b_full + sb, smem_b + (size_t)sb * b_bytes, 0, cn, j);
-              if (++sb == (uint32_t)p.b_stages) { sb = 0; phb ^= 1u; }
             }
+            if (++sb == (uint32_t)p.b_stages) { sb = 0; phb ^= 1u; }
           }
         }
-        first = false;
       }
+      first = false;
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
