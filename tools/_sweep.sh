@@ -1,5 +1,3 @@
-python -m pytest tests/test_gpu_conv.py -x -q 2>&1 | tail -3
-python tools/bench_conv.py --no-cudnn | python -c "
+for i in 0 4 2; do for dbg in 0 1 2 3; do KB_CONV_DEBUG=$dbg python tools/bench_conv.py --no-cudnn --only $i | python -c "
 import json,sys
-for l in sys.stdin:
-    d=json.loads(l); print(d['case'], round(d['ms']*1000,1), round(d['frac_tf32_peak'],3))"
+d=json.loads(sys.stdin.read()); print('debug', $dbg, d['case'], round(d['ms']*1000,1))"; done; done
