@@ -191,7 +191,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-pipeline", action="store_true")
+    ap.add_argument("--size", default="1024x768", help="WxH of the synthetic input (BASELINE configs[3]: 3840x2160 --frames 300)")
     args = ap.parse_args()
+    global W, H, FOCAL, METRIC
+    W, H = (int(v) for v in args.size.lower().split("x"))
+    FOCAL = max(W, H) / 2.0          # dblFocal = max side / 2 like pipeline.py:26 for 1024x768
+    if (W, H) != (1024, 768) or args.frames != 150:
+        METRIC = f"novel-view frames/sec at {W}x{H}, {args.frames}-frame KBE"
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
@@ -322,7 +328,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "kbe 1024x768 -> 150-frame 3D KBE (configs[1]), per-frame render loop "
+        "config": {"workload": f"kbe {W}x{H} -> {args.frames}-frame 3D KBE (configs[{1 if (W, H) == (1024, 768) else 3}]), per-frame render loop "
                                "(process_shift..resize, utils/common.py:222-260)",
                    "frames_per_step_per_gpu": F, "points": N, "pixels": P, "poses_per_launch": renderer.batch,
                    "parallelism": f"frame-shard x{world}" + (" + NCCL broadcast of the cloud per step" if world > 1 else ""),

@@ -1,3 +1,3 @@
-for i in 0 4 2; do for dbg in 0 1 2 3; do KB_CONV_DEBUG=$dbg python tools/bench_conv.py --no-cudnn --only $i | python -c "
+for pg in 4 2 1; do KB_ACCUM_PG=$pg python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-full-pipeline | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('debug', $dbg, d['case'], round(d['ms']*1000,1))"; done; done
+d=json.loads(sys.stdin.read()); print('pg', $pg, round(d['value']), round(d['roofline']['frac'],3), {k:round(v,4) for k,v in d['stage_ms_per_launch'].items()})"; done
