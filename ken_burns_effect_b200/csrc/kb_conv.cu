@@ -571,41 +571,77 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
     uint32_t sa = 0, pha = 0, a_lo = a_base_lo;
     uint32_t sb = 0, phb = 0, b_lo = b_base_lo;
     uint32_t as = 0, phacc = 0;
-    bool first = true;
     const int n_items = blockIdx.x < p.work_items ? (int)((p.work_items - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
-    for (int item = 0; item < n_items; ++item) {
-      mbar_wait(acc_empty + as, phacc ^ 1u);
+    // Shared-memory addresses fit the 14-bit (>> 4) address field, whose bits are zero in the templates: "template | address"
+    // is "template + address", and the step from one MMA to the next is a compile-time constant added to a per-slot base.
+    if (p.resident) {
+      // filters stay in shared memory: wait once for all panels, then the loop has no weight bookkeeping at all
+      if (n_items > 0)
+        for (int j = 0; j < p.b_stages; ++j) mbar_wait(b_full + j, 0);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * (uint32_t)p.Npad;
-      if (p.resident) { sb = 0; b_lo = b_base_lo; }     // resident panels: slot index = ck*taps + tap, loaded once
-      for (int ck = 0; ck < p.chunks; ++ck) {
-        mbar_wait(a_full + sa, pha);
+      for (int item = 0; item < n_items; ++item) {
+        mbar_wait(acc_empty + as, phacc ^ 1u);
         tc_fence_after();
-#pragma unroll
-        for (int tap = 0; tap < kTaps; ++tap) {
-          if (!p.resident || first) {
-            mbar_wait(b_full + sb, phb);
-            tc_fence_after();
-          }
-          const uint32_t a_off = (uint32_t)(((tap / KS) * kPitch + (tap % KS)) * kChunk * 4) >> 4;   // compile-time
+        const uint32_t d_tmem = tmem_base + as * (uint32_t)p.Npad;
+        uint32_t B0 = b_tl + b_base_lo;                       // panel (ck, tap) at slot ck * taps + tap
+        for (int ck = 0; ck < p.chunks; ++ck) {
+          mbar_wait(a_full + sa, pha);
+          tc_fence_after();
+          const uint32_t A0 = a_tl + a_lo;
           if (leader && !(p.debug & 2)) {
 #pragma unroll
-            for (int k = 0; k < kChunk / 8; ++k)
-              umma_tf32_lh(d_tmem, a_tl | ((a_lo + a_off + 2 * k) & 0x3FFF), a_hi, b_tl | ((b_lo + 2 * k) & 0x3FFF), b_hi, idesc,
-                           (uint32_t)((ck != 0) | (tap != 0) | (k != 0)));
+            for (int tap = 0; tap < kTaps; ++tap) {
+              const uint32_t a_off = (uint32_t)(((tap / KS) * kPitch + (tap % KS)) * kChunk * 4) >> 4;   // compile-time
+#pragma unroll
+              for (int k = 0; k < kChunk / 8; ++k)
+                umma_tf32_lh(d_tmem, A0 + a_off + 2 * k, a_hi, B0 + 2 * k, b_hi, idesc, (uint32_t)((ck != 0) | (tap != 0) | (k != 0)));
+              B0 += b_step_lo;
+            }
+          } else {
+            B0 += kTaps * b_step_lo;
           }
-          if (!p.resident && leader) umma_commit(b_empty + sb);
-          b_lo += b_step_lo;
-          if (++sb == (uint32_t)p.b_stages) { sb = 0; phb ^= (p.resident ? 0u : 1u); b_lo = b_base_lo; }
+          if (leader) umma_commit(a_empty + sa);
+          a_lo += kAStage >> 4;
+          if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; a_lo = a_base_lo; }
         }
-        if (leader) umma_commit(a_empty + sa);
-        a_lo += kAStage >> 4;
-        if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; a_lo = a_base_lo; }
+        if (leader) umma_commit(acc_full + as);
+        as ^= 1u;
+        if (as == 0) phacc ^= 1u;
       }
-      if (leader) umma_commit(acc_full + as);
-      as ^= 1u;
-      if (as == 0) phacc ^= 1u;
-      first = false;
+    } else {
+      for (int item = 0; item < n_items; ++item) {
+        mbar_wait(acc_empty + as, phacc ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * (uint32_t)p.Npad;
+        for (int ck = 0; ck < p.chunks; ++ck) {
+          mbar_wait(a_full + sa, pha);
+          tc_fence_after();
+          const uint32_t A0 = a_tl + a_lo;
+#pragma unroll
+          for (int tap = 0; tap < kTaps; ++tap) {
+            mbar_wait(b_full + sb, phb);
+            tc_fence_after();
+            const uint32_t a_off = (uint32_t)(((tap / KS) * kPitch + (tap % KS)) * kChunk * 4) >> 4;   // compile-time
+            if (leader) {
+              const uint32_t B0 = b_tl + b_lo;
+              if (!(p.debug & 2)) {
+#pragma unroll
+                for (int k = 0; k < kChunk / 8; ++k)
+                  umma_tf32_lh(d_tmem, A0 + a_off + 2 * k, a_hi, B0 + 2 * k, b_hi, idesc, (uint32_t)((ck != 0) | (tap != 0) | (k != 0)));
+              }
+              umma_commit(b_empty + sb);
+            }
+            b_lo += b_step_lo;
+            if (++sb == (uint32_t)p.b_stages) { sb = 0; phb ^= 1u; b_lo = b_base_lo; }
+          }
+          if (leader) umma_commit(a_empty + sa);
+          a_lo += kAStage >> 4;
+          if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; a_lo = a_base_lo; }
+        }
+        if (leader) umma_commit(acc_full + as);
+        as ^= 1u;
+        if (as == 0) phacc ^= 1u;
+      }
     }
   } else {
     // ===== epilogue warps =====

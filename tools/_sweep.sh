@@ -1,3 +1,5 @@
-for pg in 4 2 1; do KB_ACCUM_PG=$pg python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-full-pipeline | python -c "
+python -m pytest tests/test_gpu_conv.py -x -q 2>&1 | tail -3
+python tools/bench_conv.py --no-cudnn | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('pg', $pg, round(d['value']), round(d['roofline']['frac'],3), {k:round(v,4) for k,v in d['stage_ms_per_launch'].items()})"; done
+for l in sys.stdin:
+    d=json.loads(l); print(d['case'], round(d['ms']*1000,1), round(d['frac_tf32_peak'],3))"
