@@ -175,6 +175,7 @@ struct ConvKernelParams {
   int tile_w, tile_h, tiles_x, tiles_y;
   int chunks, ksize, stride, pad;
   int Cout, Cout4;      // real output channels, and rounded up to 4 (allocated)
+  int last_ksteps;      // 8-channel MMA steps that hold real channels in the LAST 32-channel slice (1..4): the rest is zero padding
   int cpad;             // Cout rounded up to a whole number of N blocks (size of the epilogue tables in shared memory)
   int Npad;             // UMMA N of this launch
   int stages;
@@ -400,14 +401,18 @@ __global__ void __launch_bounds__(kConvThreads) k_conv_tf32(const __grid_constan
     const uint32_t d_hi = (uint32_t)(tmpl >> 32), d_tl = (uint32_t)tmpl;
     const uint32_t base_lo = smem_u32(smem) >> 4, stage_lo = (uint32_t)stage_bytes >> 4;
     uint32_t s = 0, ph = 0, lo = base_lo;
+    int ck = 0;
     for (int j = 0; j < J; ++j) {
       mbar_wait(full + s, ph);
       tc_fence_after();
+      const int ksteps = ck == p.chunks - 1 ? p.last_ksteps : kChunk / 8;   // skip MMA steps made of padding channels only
+      if (++ck == p.chunks) ck = 0;
       if (leader) {
 #pragma unroll
         for (int k = 0; k < kChunk / 8; ++k)   // UMMA K = 8 tf32 = 32 bytes: advance the start address inside the swizzle row
-          umma_tf32_lh(tmem_base, d_tl | ((lo + 2 * k) & 0x3FFF), d_hi, d_tl | ((lo + (kABytes >> 4) + 2 * k) & 0x3FFF), d_hi, idesc,
-                       (uint32_t)((j | k) != 0));
+          if (k < ksteps)
+            umma_tf32_lh(tmem_base, d_tl | ((lo + 2 * k) & 0x3FFF), d_hi, d_tl | ((lo + (kABytes >> 4) + 2 * k) & 0x3FFF), d_hi, idesc,
+                         (uint32_t)((j | k) != 0));
         umma_commit(empty + s);                // slot reusable once these MMAs have read it
       }
       lo += stage_lo;
@@ -588,13 +593,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
           mbar_wait(a_full + sa, pha);
           tc_fence_after();
           const uint32_t A0 = a_tl + a_lo;
+          const int ksteps = ck == p.chunks - 1 ? p.last_ksteps : kChunk / 8;   // skip MMA steps made of padding channels only
           if (leader && !(p.debug & 2)) {
 #pragma unroll
             for (int tap = 0; tap < kTaps; ++tap) {
               const uint32_t a_off = (uint32_t)(((tap / KS) * kPitch + (tap % KS)) * kChunk * 4) >> 4;   // compile-time
 #pragma unroll
               for (int k = 0; k < kChunk / 8; ++k)
-                umma_tf32_lh(d_tmem, A0 + a_off + 2 * k, a_hi, B0 + 2 * k, b_hi, idesc, (uint32_t)((ck != 0) | (tap != 0) | (k != 0)));
+                if (k < ksteps)
+                  umma_tf32_lh(d_tmem, A0 + a_off + 2 * k, a_hi, B0 + 2 * k, b_hi, idesc, (uint32_t)((ck != 0) | (tap != 0) | (k != 0)));
               B0 += b_step_lo;
             }
           } else {
@@ -626,8 +633,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
               const uint32_t B0 = b_tl + b_lo;
               if (!(p.debug & 2)) {
 #pragma unroll
-                for (int k = 0; k < kChunk / 8; ++k)
-                  umma_tf32_lh(d_tmem, A0 + a_off + 2 * k, a_hi, B0 + 2 * k, b_hi, idesc, (uint32_t)((ck != 0) | (tap != 0) | (k != 0)));
+                for (int k = 0; k < kChunk / 8; ++k)   // (streamed filters = wide layers: no padding steps worth skipping)
+                    umma_tf32_lh(d_tmem, A0 + a_off + 2 * k, a_hi, B0 + 2 * k, b_hi, idesc, (uint32_t)((ck != 0) | (tap != 0) | (k != 0)));
               }
               umma_commit(b_empty + sb);
             }
@@ -986,6 +993,7 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
   KB_REQUIRE(algo == 1 || (algo == 2 && halo_ok), "kb_conv2d: algo 2 needs stride 1, ksize <= 3, 'same' padding");
 
   p.chunks = (a->Cin + kChunk - 1) / kChunk;
+  p.last_ksteps = ((a->Cin - (p.chunks - 1) * kChunk) + 7) / 8;
   p.ksize = a->ksize;
   p.stride = a->stride;
   p.pad = a->pad;
