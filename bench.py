@@ -115,6 +115,33 @@ def full_pipeline(steps=3, warmup=2, frames=150):
             "count and hole statistics are not those of a trained model; CNN forwards replay from CUDA graphs after 2 calls"}
 
 
+def cpu_cnn_stage():
+    """The CNN forwards of one KBE on the host cores: the nn.Module mirrors run plain torch fp32 on CPU tensors -- the same
+    layers, shapes and arithmetic as the reference's modules (tests/test_models_cpu.py checks them against fixtures made by the
+    reference itself).  One timed call each after a small-size warm-up; -> seconds per KBE (Semantics + Disparity + Refine +
+    2 x (context + Inpaint.forward)), thread count."""
+    import torch
+    from ken_burns_effect_b200.models.disparity_estimation import Disparity, Semantics
+    from ken_burns_effect_b200.models.disparity_refinement import Refine
+    from ken_burns_effect_b200.models.pointcloud_inpainting import Inpaint
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    with torch.no_grad():
+        sem, dis, ref, inp = Semantics().eval(), Disparity().eval(), Refine().eval(), Inpaint().eval()
+        small = torch.rand(1, 3, 64, 64)
+        dis(small, sem(small))                                   # warm the thread pool / oneDNN primitives
+        img, half = torch.rand(1, 3, H, W), torch.rand(1, 3, H // 2, W // 2)
+        t0 = time.perf_counter()
+        d = dis(half, sem(half))
+        t1 = time.perf_counter()
+        ref(img, d)
+        t2 = time.perf_counter()
+        mask = (torch.rand(1, 1, H, W) > 0.1).float()
+        inp(mask, tensorImage=img * mask, tensorDisparity=torch.rand(1, 1, H, W) * mask)
+        t3 = time.perf_counter()
+    return (t1 - t0) + (t2 - t1) + 2.0 * (t3 - t2), torch.get_num_threads()
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU with NVML while the timed region runs."""
 
@@ -359,6 +386,17 @@ def main():
             out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                    "sample": f"{n} frames of the same 150-pose path (spread over it), same cloud, "
                                              f"{dt:.1f} s of CPU work, all host threads"}
+            full = out.get("kbe_full_pipeline")
+            if isinstance(full, dict) and "error" not in full:
+                try:
+                    cnn_s, threads = cpu_cnn_stage()
+                    total_s = cnn_s + args.frames / fps
+                    full["cpu_baseline"] = {"value": args.frames / total_s, "unit": "frames/s", "cores": threads, "kind": "port",
+                                            "s_per_kbe": total_s, "s_cnn_stage": cnn_s,
+                                            "sample": "one timed CPU forward of each network at the KBE's shapes (torch fp32, all "
+                                                      "threads; Inpaint counted twice) + the render loop at the CPU frames/s above"}
+                except Exception as e:
+                    full["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

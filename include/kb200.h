@@ -91,6 +91,10 @@ int kb_fill(const float *input, const float *depth, float *output, int B, int C,
 /* out = median5x5(in) for in in {0,1} (reflect padding) == (5x5 box count >= 13). in/out [B,1,H,W]. */
 int kb_median5_binary(const float *in, float *out, int B, int H, int W, kb_stream_t stream);
 
+/* spatial_filter(x, 'laplacian'), utils/common.py:398-409: the reference's 5-tap kernel on a replicate-padded map, applied to
+ * each of `planes` = B*C planes [H,W] independently (the reference builds a block-diagonal conv2d for it). */
+int kb_laplacian5(const float *in, float *out, int planes, int H, int W, kb_stream_t stream);
+
 /* ---- the per-frame loop of process_kenburns, utils/common.py:222-260, fused ---------------------- */
 
 typedef struct kb_pose {

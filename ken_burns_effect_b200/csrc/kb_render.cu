@@ -246,6 +246,25 @@ __global__ void __launch_bounds__(256) k_fill(const float *__restrict__ input, c
   for (int c = 0; c < C; ++c) out[(long)c * P + me] = in[(long)c * P + from];
 }
 
+
+// spatial_filter(x, 'laplacian'), utils/common.py:398-409: the reference's asymmetric 5-tap kernel (taps (0,1) = -1,
+// (0,2) = -1, (1,1) = 4, (1,0) = -1, (2,0) = -1 of a 3x3 window) on a replicate-padded map, one channel at a time.
+// The reference runs it as F.conv2d (cuDNN); the sum below keeps cuDNN's-agnostic left-to-right order of the five products.
+__global__ void __launch_bounds__(256) k_laplacian5(const float *__restrict__ in, float *__restrict__ out, int H, int W) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  const float *p = in + (long)blockIdx.z * H * W;
+  const int xm = max(x - 1, 0), xp = min(x + 1, W - 1), ym = max(y - 1, 0), yp = min(y + 1, H - 1);
+  // window rows: y-1 -> taps (0,1) at x, (0,2) at x+1;  y -> (1,0) at x-1, (1,1) at x;  y+1 -> (2,0) at x-1
+  float acc = -p[(long)ym * W + x];
+  acc = __fsub_rn(acc, p[(long)ym * W + xp]);
+  acc = __fsub_rn(acc, p[(long)y * W + xm]);
+  acc = __fmaf_rn(4.0f, p[(long)y * W + x], acc);
+  acc = __fsub_rn(acc, p[(long)yp * W + xm]);
+  out[(long)blockIdx.z * H * W + (long)y * W + x] = acc;
+}
+
 // median-5 on a {0,1} map with reflect padding == (5x5 count >= 13), :417-421.
 __global__ void __launch_bounds__(256) k_median5_binary(const float *__restrict__ in, float *__restrict__ out, int H, int W) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -471,6 +490,14 @@ int kb_median5_binary(const float *in, float *out, int B, int H, int W, kb_strea
   k_median5_binary<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, H, W);
   count_launch();
   return check_launch("kb_median5_binary");
+}
+
+int kb_laplacian5(const float *in, float *out, int planes, int H, int W, kb_stream_t stream) {
+  KB_REQUIRE(in && out && in != out && planes > 0 && H > 0 && W > 0, "kb_laplacian5: bad arguments");
+  dim3 grid(cdiv(W, 32), cdiv(H, 8), planes);
+  k_laplacian5<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, H, W);
+  count_launch();
+  return check_launch("kb_laplacian5");
 }
 
 int kb_selftest_arith(int which, const float *a, const float *b, long n, int W, unsigned long long *mismatches,

@@ -60,6 +60,12 @@ _LAPLACE_TAPS = ((0, 1, -1.0), (0, 2, -1.0), (1, 1, 4.0), (1, 0, -1.0), (2, 0, -
 def spatial_filter(tensorInput, strType):
     """utils/common.py:394-426: 'laplacian' (the reference's asymmetric 5-tap kernel, replicate padding),
     'median-3' / 'median-5' (reflect padding)."""
+    if strType == 'laplacian' and tensorInput.is_cuda and tensorInput.dtype == torch.float32:
+        x = tensorInput.contiguous()
+        out = torch.empty_like(x)
+        B, C, H, W = x.shape
+        nat.check(nat.lib().kb_laplacian5(_ptr(x), _ptr(out), B * C, H, W, _stream()), "kb_laplacian5")
+        return out
     if strType == 'laplacian':
         C = tensorInput.size(1)
         k = tensorInput.new_zeros(C, C, 3, 3)

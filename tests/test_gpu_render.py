@@ -162,3 +162,18 @@ def test_negative_error_branch():
     o = oracle.splat_min(pts, H, W, focal, 120)
     assert np.array_equal(zraw.cpu().numpy().view(np.int32), o.view(np.int32))
     assert (o < 0).any()
+
+
+def test_laplacian_kernel_vs_torch_conv():
+    """kb_laplacian5 against the reference's formulation of spatial_filter(x, 'laplacian') (F.conv2d with the 5-tap kernel
+    on a replicate-padded map, utils/common.py:398-409), evaluated by torch on the CPU."""
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(2, 3, 37, 53, generator=g) * 4
+    ref = kb.spatial_filter(x, 'laplacian')                 # CPU tensors take the torch path
+    got = kb.spatial_filter(x.cuda(), 'laplacian').cpu()
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max()) <= 4e-6           # five fp32 terms of magnitude <= 16
+    # the kernel is asymmetric: a unit ramp along x gives -x - (x+1) - (x-1) + 4x - (x-1) = 1 away from the border
+    ramp = torch.arange(53, dtype=torch.float32).view(1, 1, 1, 53).expand(1, 1, 9, 53).contiguous()
+    lap = kb.spatial_filter(ramp.cuda(), 'laplacian').cpu()
+    assert torch.equal(lap[..., 1:-1, 1:-1], torch.ones(1, 1, 7, 51))
