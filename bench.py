@@ -76,7 +76,7 @@ def cpu_baseline(budget_s=12.0, max_frames=300, threads=0):
     return n / dt, oracle.max_threads(), dt, n
 
 
-def full_pipeline(steps=3, warmup=2, frames=150):
+def full_pipeline(steps=3, warmup=3, frames=150):
     """BASELINE configs[1] end to end: one 1024x768 image in HOST memory -> Semantics/Disparity/Refine (tcgen05 convs) ->
     two pointcloud_inpainting passes -> 150 rendered uint8 frames in pinned HOST memory, through Pipeline (the call
     kbe.py makes).  Random-init weights (no checkpoints offline), synthetic image.  -> dict for the JSON line."""
@@ -112,7 +112,7 @@ def full_pipeline(steps=3, warmup=2, frames=150):
     return {"value": frames * steps / total, "unit": "frames/s", "ms_per_kbe": 1e3 * total / steps,
             "ms_cnn_and_inpaint_stage": 1e3 * t_cnn / steps, "ms_render_loop": 1e3 * t_render / steps, "points": int(npts),
             "conv_tflop_per_kbe": 2.30, "note": "random-init weights: the disparity is noise-like, so the appended point "
-            "count and hole statistics are not those of a trained model; CNN forwards replay from CUDA graphs after 2 calls"}
+            "count and hole statistics are not those of a trained model; CNN forwards replay from CUDA graphs from their 4th call on (captured during warm-up)"}
 
 
 def cpu_cnn_stage():
@@ -196,7 +196,7 @@ def run_reference(args):
     sample = nframes
     desc = (f"~{sample} of the 150 poses per step (spread over the path, {per_step:.0f} s of CPU work per step), "
             f"full 1024x768 cloud incl. stand-in inpainted points")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sample / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -205,7 +205,29 @@ def run_reference(args):
                            "of its kernels + its numpy/OpenCV tail (oracle/kb_oracle.c)"},
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner on communicator creation, for
+    one) are sent to stderr for the duration of the run; emit() writes the result to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, line)
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
@@ -226,6 +248,7 @@ def main():
     if (W, H) != (1024, 768) or args.frames != 150:
         METRIC = f"novel-view frames/sec at {W}x{H}, {args.frames}-frame KBE"
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -243,7 +266,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL logs to stdout by default; stdout carries ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     pts, rgb, dep, common, poses, (cw, ch) = build_workload(args.frames, world, rank)
@@ -397,7 +420,7 @@ def main():
                                                       "threads; Inpaint counted twice) + the render loop at the CPU frames/s above"}
                 except Exception as e:
                     full["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 

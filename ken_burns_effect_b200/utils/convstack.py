@@ -295,14 +295,17 @@ def grid_forward_nhwc(module, features, stem, semantics_res=None):
 # -----------------------------------------------------------------------------------------------------------------
 # CUDA-graph replay of a whole network forward
 # -----------------------------------------------------------------------------------------------------------------
-# A network forward is 60-130 launches issued from Python through ctypes.  The forwards are pure functions of their input
-# tensors with static shapes, so they can be captured into a CUDA graph and replayed with one cudaGraphLaunch.  Measured on
-# B200 (profiles/bench_nets_r01h.md): the host stays ahead of the GPU even in eager mode (Inpaint 5.33 ms eager vs 5.36 ms
-# replayed, Disparity 2.60 vs 2.27 ms), so replay is OFF by default (KB_GRAPHS=1 turns it on; it pays off when the host is
-# slow or busy).
+# A network forward is 60-130 launches issued from Python through ctypes (~30 us of host time each).  In isolation the host
+# stays ahead of the GPU (profiles/bench_nets_r01h.md: Inpaint 5.33 ms eager vs 5.36 ms replayed), but inside the pipeline every
+# host sync (.item(), nonzero, minMaxLoc) drains the queue and the GPU then waits for the host to refill it: the CNN stage of
+# a KBE takes 22.5 ms eager and 20.8 ms with the forwards replayed from CUDA graphs.  The forwards are pure functions of their
+# input tensors with static shapes, so from the THIRD call with the same shapes and weights on they are captured and replayed
+# (a single image -- two inpainting passes -- never pays the capture; a server processing a stream of images does once).
+# KB_GRAPHS=0 disables it.
 import os as _os
 
-GRAPHS_ENABLED = _os.environ.get("KB_GRAPHS", "0") == "1"
+GRAPHS_ENABLED = _os.environ.get("KB_GRAPHS", "1") != "0"
+GRAPH_EAGER_CALLS = 2
 
 
 def _fingerprint(owner):
@@ -310,9 +313,10 @@ def _fingerprint(owner):
 
 
 def graphed(owner, tag, fn, *tensors):
-    """fn(*tensors) -> tensor or tuple of tensors, replayed from a CUDA graph from the third call on (first call eager:
-    packs weights and warms the allocator; second call: capture).  Outputs are fresh tensors (copies of the graph's static
-    outputs).  The graph is dropped when a parameter of `owner` changes (load_state_dict, .to())."""
+    """fn(*tensors) -> tensor or tuple of tensors; eager for the first GRAPH_EAGER_CALLS calls with a given signature (they
+    also pack the weights and warm the allocator), captured into a CUDA graph on the next one and replayed afterwards.
+    Outputs are fresh tensors (copies of the graph's static outputs).  The graph is dropped when the input shapes or any
+    parameter of `owner` change (load_state_dict, .to())."""
     if not GRAPHS_ENABLED or not tensors[0].is_cuda or torch.cuda.is_current_stream_capturing():
         return fn(*tensors)
     store = owner.__dict__.get('_kb_graphs')          # lives and dies with the module (not a registered attribute)
@@ -322,9 +326,11 @@ def graphed(owner, tag, fn, *tensors):
     sig = (tuple((tuple(t.shape), t.dtype, t.device.index) for t in tensors), _fingerprint(owner))
     ent = store.get(tag)
     if ent is None or ent['sig'] != sig:
-        store[tag] = {'sig': sig, 'graph': None}
-        return fn(*tensors)
+        ent = store[tag] = {'sig': sig, 'graph': None, 'calls': 0}
     if ent['graph'] is None:
+        ent['calls'] += 1
+        if ent['calls'] <= GRAPH_EAGER_CALLS:
+            return fn(*tensors)
         static_in = [t.clone() for t in tensors]
         torch.cuda.current_stream().synchronize()
         g = torch.cuda.CUDAGraph()
