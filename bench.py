@@ -264,6 +264,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the render path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
+    if world > 1:
+        from ken_burns_effect_b200.utils import shard as _shard
+        numa = _shard.bind_to_gpu_numa_node(local)       # before any pinned allocation
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -382,6 +386,7 @@ def main():
                                "(process_shift..resize, utils/common.py:222-260)",
                    "frames_per_step_per_gpu": F, "points": N, "pixels": P, "poses_per_launch": renderer.batch,
                    "parallelism": f"frame-shard x{world}" + (" + NCCL broadcast of the cloud per step" if world > 1 else ""),
+                   "cpu_affinity": (f"rank 0 bound to {len(numa)} cores near its GPU (NVML)" if numa else "unbound"),
                    "l2": "no explicit flush: each step streams ~0.8 GB of z-buffers/accumulators/frames (> 126 MB L2)"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(packed_host.numel() * 4) if rank == 0 else 0,

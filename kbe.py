@@ -105,6 +105,8 @@ def init_distributed():
     if world > 1 and not torch.distributed.is_initialized():
         local = int(os.environ.get('LOCAL_RANK', '0'))
         torch.cuda.set_device(local)
+        from ken_burns_effect_b200.utils import shard
+        shard.bind_to_gpu_numa_node(local)
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         torch.distributed.init_process_group('nccl', device_id=torch.device('cuda', local))
     return world
