@@ -91,6 +91,15 @@ int kb_fill(const float *input, const float *depth, float *output, int B, int C,
 /* out = median5x5(in) for in in {0,1} (reflect padding) == (5x5 box count >= 13). in/out [B,1,H,W]. */
 int kb_median5_binary(const float *in, float *out, int B, int H, int W, kb_stream_t stream);
 
+/* ---- generate_mask, utils/common.py:689-830 (training-time disocclusion mask) -------------------------------------- */
+/* xyz [B,3,N] (points already shifted, :690) -> mask [B,N]: 1 where the point owns the z-buffer cell of the pixel it votes for.
+ * The reference's check-then-atomicMin / atomicExch bookkeeping races; this is its outcome for threads running in index order
+ * (the lowest-indexed point among those with the minimal err wins a pixel).  The caller applies the median-5
+ * (:829, kb_median5_binary).  workspace: kb_mask_workspace_bytes() bytes. */
+size_t kb_mask_workspace_bytes(int B, long N, int H, int W);
+int kb_generate_mask(const float *xyz, int B, long N, double focal, double baseline, int H, int W, float *mask, void *workspace,
+                     kb_stream_t stream);
+
 /* spatial_filter(x, 'laplacian'), utils/common.py:398-409: the reference's 5-tap kernel on a replicate-padded map, applied to
  * each of `planes` = B*C planes [H,W] independently (the reference builds a block-diagonal conv2d for it). */
 int kb_laplacian5(const float *in, float *out, int planes, int H, int W, kb_stream_t stream);

@@ -56,6 +56,8 @@ SIGNATURES = {
                                      c_void, c_void, c_void, c_void]),
     "kb_fill": (c_int, [c_void, c_void, c_void, c_int, c_int, c_int, c_int, c_void]),
     "kb_median5_binary": (c_int, [c_void, c_void, c_int, c_int, c_int, c_void]),
+    "kb_mask_workspace_bytes": (c_size_t, [c_int, c_long, c_int, c_int]),
+    "kb_generate_mask": (c_int, [c_void, c_int, c_long, c_double, c_double, c_int, c_int, c_void, c_void, c_void]),
     "kb_laplacian5": (c_int, [c_void, c_void, c_int, c_int, c_int, c_void]),
     "kb_frames_workspace_bytes": (c_size_t, [ctypes.POINTER(KBFrameParams), c_int]),
     "kb_render_frames": (c_int, [c_void, c_void, c_long, ctypes.POINTER(KBPose), c_int,

@@ -287,6 +287,47 @@ __global__ void __launch_bounds__(256) k_median5_binary(const float *__restrict_
 }
 
 
+
+// ---- generate_mask, utils/common.py:689-830 -----------------------------------------------------------------------------
+// The reference marks, per point, whether it ended up owning the z-buffer cell it votes for, with a check-then-atomicMin
+// and an atomicExch of point ids that race.  Deterministic form of the same bookkeeping, three passes:
+// k_splat_min (z-buffer + the pixel each point votes for), k_mask_winner (lowest point index among the points that hold the
+// minimal err of their pixel), k_mask_write (mask = 1 for the winner; point 0 keeps a 1 whenever it ever lowered its cell,
+// the reference's `pid > 0` quirk, :759).  This is what the reference computes when its threads happen to run in index order.
+__global__ void __launch_bounds__(256) k_mask_winner(const float *__restrict__ xyz, long N, Camera cam, const float *__restrict__ zee,
+                                                     const int32_t *__restrict__ pix_idx, int *__restrict__ winner) {
+  const int b = blockIdx.y;
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int pix = pix_idx[(long)b * N + n];
+  if (pix < 0) return;
+  const float *s = xyz + (long)b * 3 * N;
+  Proj p;
+  if (!project(__ldg(s + n), __ldg(s + N + n), __ldg(s + 2 * N + n), cam, p)) return;
+  const long P = (long)cam.H * cam.W;
+  if (p.err == zee[(long)b * P + pix]) atomicMin(winner + (long)b * P + pix, (int)n);
+}
+
+__global__ void __launch_bounds__(256) k_mask_write(long N, long P, const int32_t *__restrict__ pix_idx, const int *__restrict__ winner,
+                                                    float *__restrict__ mask) {
+  const int b = blockIdx.y;
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int pix = pix_idx[(long)b * N + n];
+  float m = 0.0f;
+  if (pix >= 0) {
+    // in index order point 0 is the first to reach its pixel, so it always lowers the cell (1e6 > err) and is never cleared
+    m = (winner[(long)b * P + pix] == (int)n || n == 0) ? 1.0f : 0.0f;
+  }
+  mask[(long)b * N + n] = m;
+}
+
+__global__ void __launch_bounds__(256) k_fill_i32(int *__restrict__ p, long n, int v) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
 // ---- self-test of the exact fp32 replacements in kb_common.cuh / kb_frames.cu against the literal forms -----------
 __device__ __forceinline__ unsigned char st_quant(float acc, float den) {
   float v = __fmul_rn(__fdiv_rn(acc, den), 255.0f);
@@ -490,6 +531,28 @@ int kb_median5_binary(const float *in, float *out, int B, int H, int W, kb_strea
   k_median5_binary<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, H, W);
   count_launch();
   return check_launch("kb_median5_binary");
+}
+
+size_t kb_mask_workspace_bytes(int B, long N, int H, int W) {
+  return sizeof(float) * (size_t)B * H * W + sizeof(int) * (size_t)B * H * W + sizeof(int32_t) * (size_t)B * (size_t)N;
+}
+
+int kb_generate_mask(const float *xyz, int B, long N, double focal, double baseline, int H, int W, float *mask, void *workspace,
+                     kb_stream_t stream) {
+  KB_REQUIRE(xyz && mask && workspace && B > 0 && N > 0 && H > 0 && W > 0 && N < (1L << 31), "kb_generate_mask: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long P = (long)H * W;
+  float *zee = (float *)workspace;
+  int *winner = (int *)(zee + (size_t)B * P);
+  int32_t *pix = (int32_t *)(winner + (size_t)B * P);
+  int rc = kb_splat_min(xyz, B, N, nullptr, focal, baseline, zee, H, W, pix, stream);
+  if (rc) return rc;
+  k_fill_i32<<<min(cdiv((long)B * P, 256), 148u * 8u), 256, 0, st>>>(winner, (long)B * P, 0x7fffffff);
+  dim3 grid(cdiv(N, 256), B);
+  k_mask_winner<<<grid, 256, 0, st>>>(xyz, N, make_camera(focal, baseline, H, W), zee, pix, winner);
+  k_mask_write<<<grid, 256, 0, st>>>(N, P, pix, winner, mask);
+  count_launch(3);
+  return check_launch("kb_generate_mask");
 }
 
 int kb_laplacian5(const float *in, float *out, int planes, int H, int W, kb_stream_t stream) {

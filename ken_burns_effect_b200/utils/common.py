@@ -146,6 +146,24 @@ def accumulate_with_zee(tensorInput, tensorData, tensorZee, dblFocal, dblBaselin
     return render, existing
 
 
+def generate_mask(tensorInput, tensorShift, intWidth, intHeight, dblFocal, dblBaseline):
+    """utils/common.py:689-830: which points of the grid cloud [B,3,H*W] stay visible after the camera shift -> [B,1,H,W]
+    (1 = the point owns the z-buffer cell it projects to), median-5 filtered.  The reference's kernel races; this is its
+    deterministic index-order outcome (include/kb200.h: kb_generate_mask).  Training-time helper (utils/utils.py:285-287)."""
+    pts = (tensorInput + tensorShift).contiguous()
+    _need_cuda(pts)
+    B, _, N = pts.shape
+    H, W = int(intHeight), int(intWidth)
+    if N != H * W:
+        raise RuntimeError(f"generate_mask: the cloud must be the H*W grid ({H * W} points), got {N}")   # :829 views it as an image
+    L = nat.lib()
+    mask = torch.empty(B, N, device=pts.device, dtype=torch.float32)
+    ws = torch.empty(L.kb_mask_workspace_bytes(B, N, H, W), device=pts.device, dtype=torch.uint8)
+    nat.check(L.kb_generate_mask(_ptr(pts), B, N, float(dblFocal), float(dblBaseline), H, W, _ptr(mask), _ptr(ws), _stream()),
+              "kb_generate_mask")
+    return spatial_filter(mask.view(-1, 1, H, W), 'median-5')
+
+
 def fill_disocclusion(tensorInput, tensorDepth):
     """utils/common.py:833-937.  [B,C,H,W], [B,1,H,W] -> filled copy of the input."""
     _need_cuda(tensorInput, tensorDepth)

@@ -74,6 +74,17 @@ def splat_min(xyz, H, W, focal, baseline, want_idx=False):
     return (zee, idx) if want_idx else zee
 
 
+def mask_zee(xyz, H, W, focal, baseline):
+    """The kernel of generate_mask (common.py:696-827) in index order. xyz [B,3,N] (already shifted) -> mask [B,N]."""
+    xyz, px = _f32(xyz)
+    B, _, N = xyz.shape
+    mask = np.empty((B, N), np.float32)
+    zee = np.empty((B, H, W), np.float32)
+    lib().kbo_mask_zee(px, B, ctypes.c_long(N), ctypes.c_double(focal), ctypes.c_double(baseline), H, W,
+                       mask.ctypes.data_as(c_f32p), zee.ctypes.data_as(c_f32p))
+    return mask
+
+
 def degrid(zee, mode=0):
     """updateDegrid (common.py:524-568). mode 0 = race-free (canonical), 1 = in-place raster order."""
     zee, pz = _f32(zee)

@@ -164,6 +164,45 @@ KBO_API void kbo_splat_min(const float *xyz, int B, long N, double focal, double
   }
 }
 
+/* generate_mask's kernel (common.py:696-827), sequential semantics.  The reference runs one thread per point: a point that
+ * finds the cell of the pixel it votes for strictly behind its own err lowers the cell, sets its own mask to 1, swaps its
+ * index into id_memory and clears the mask of the point it displaced (unless that was point 0: `pid > 0`, :759); a point
+ * that does not lower the cell clears its own mask.  Threads race (check-then-atomicMin), so the reference's result
+ * depends on scheduling; this restatement executes the points in index order, one outcome the race allows and the
+ * canonical one this repository adopts: mask[n] = 1 iff n is the LOWEST-indexed point among those with the minimal err
+ * at its pixel -- except that a displaced point 0 keeps its 1, like in the reference.  mask [B,N] (N = H*W at the call
+ * site, :829), zee [B,H,W] scratch. */
+KBO_API void kbo_mask_zee(const float *xyz, int B, long N, double focal, double baseline, int H, int W, float *mask,
+                          float *zee) {
+  const long P = (long)H * W;
+  int32_t *ids = (int32_t *)malloc(sizeof(int32_t) * (size_t)P);
+  for (long b = 0; b < B; ++b) {
+    float *z = zee + b * P, *m = mask + b * N;
+    const float *s = xyz + b * 3 * N;
+    for (long i = 0; i < P; ++i) { z[i] = 1000000.0f; ids[i] = -1; }
+    for (long n = 0; n < N; ++n) m[n] = 0.0f;
+    for (long n = 0; n < N; ++n) {
+      kbo_proj p;
+      if (!kbo_project(s[n], s[N + n], s[2 * N + n], focal, baseline, W, H, &p)) continue;
+      const int k = kbo_pick(&p);
+      if (k < 0) continue;
+      const int px = p.nwx + (k & 1), py = p.nwy + (k >> 1);
+      if (!((px >= 0) & (px < W) & (py >= 0) & (py < H))) continue;
+      const long pix = (long)py * W + px;
+      if (z[pix] > p.err) {
+        z[pix] = p.err;
+        m[n] = 1.0f;
+        const int32_t pid = ids[pix];
+        ids[pix] = (int32_t)n;
+        if (pid > 0) m[pid] = 0.0f;
+      } else {
+        m[n] = 0.0f;
+      }
+    }
+  }
+  free(ids);
+}
+
 /* kernel_pointrender_updateDegrid (common.py:524-568).
  * The reference updates zee IN PLACE while other threads read it (a benign race).  mode 0 restates it
  * race-free: read zee_in, write zee_out (what every thread would see if all reads came first) -- the

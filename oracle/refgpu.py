@@ -102,3 +102,21 @@ def fill_disocclusion(inp, depth, N=None, focal=None, baseline=None):
     out = inp.clone()
     _launch(row, B * H * W, [inp.contiguous(), depth.contiguous(), out])
     return out
+
+
+def mask_zee(points_shifted, W, H, focal, baseline):
+    """The kernel of the reference's generate_mask (utils/common.py:696-827) on already shifted points [B,3,N] -> the raw
+    masks [B,N] before the median filter (:829).  Racy by construction: two runs may differ."""
+    B, _, N = points_shifted.shape
+    row = None
+    for r in manifest():
+        if r["role"] == "maskZee" and r["H"] == H and r["W"] == W and r["N"] == N and r["B"] == B and abs(r["focal"] - focal) < 1e-9:
+            row = r
+            break
+    if row is None:
+        raise KeyError(f"no reference maskZee cubin for B={B} N={N} {W}x{H} f={focal}")
+    zee = points_shifted.new_zeros(B, 1, H, W).fill_(1000000.0)      # :692
+    masks = points_shifted.new_zeros(B, 1, N)                        # :693
+    ids = points_shifted.new_ones(B, H, W) * -1                      # :694 (a FLOAT tensor the kernel reads as int*)
+    _launch(row, B * N, [points_shifted.contiguous(), masks, zee, ids])
+    return masks.view(B, N)

@@ -102,3 +102,20 @@ def test_oracle_shift_points():
     assert np.array_equal(out[:, 0], np.array([2.0, 0.0, 514.0], np.float32))
     assert np.array_equal(out[:, 2], sh)          # z = 0: x*0 + shift
     assert out[0, 1] == np.float32(-2.0) * (np.float32(3.0) / (np.float32(3.0) + np.float32(1e-7))) + np.float32(0.5)
+
+
+def test_mask_zee_index_order_semantics():
+    """generate_mask's kernel in index order (oracle.mask_zee): strict '>' keeps the first of equal points, a nearer later
+    point displaces an earlier one, point 0 is never cleared (utils/common.py:755-765)."""
+    import oracle
+    W, H, focal = 8, 8, 4.0
+    pts = np.zeros((1, 3, W * H), np.float32)
+    pts[0, 2] = 0.0005
+    for n, z in ((0, 50.0), (3, 30.0), (5, 20.0), (9, 20.0), (12, 25.0)):
+        pts[0, :, n] = (0.3 * z / focal, 0.3 * z / focal, z)
+    raw = oracle.mask_zee(pts, H, W, focal, 120)
+    assert raw[0, 0] == 1.0          # displaced, but pid > 0 protects point 0
+    assert raw[0, 3] == 0.0          # displaced by 5
+    assert raw[0, 5] == 1.0          # nearest, first of the two equal points
+    assert raw[0, 9] == 0.0 and raw[0, 12] == 0.0
+    assert raw.sum() == 2.0
