@@ -213,8 +213,8 @@ struct ConvKernelParams {
 __device__ __forceinline__ float prelu1(float v, float s) { return fmaxf(v, 0.f) + s * fminf(v, 0.f); }
 
 struct EpiSmem {
-  const float *bias;              // [cpad]   (zeros when the layer has no bias)
-  const float *slope[kMaxOut];    // [cpad]   (only valid where p.out[o].slope != nullptr)
+  const float *bias;              // [cpad]   (zeros when the layer has no bias); the slopes of output o follow at
+  int cpad;                       //          bias + (1 + o) * cpad (only valid where p.out[o].slope != nullptr)
 };
 
 // floats of shared memory the epilogue tables take for `cpad` (padded) output channels
@@ -224,11 +224,11 @@ __host__ __device__ constexpr int epi_smem_floats(int cpad) { return (1 + kMaxOu
 __device__ __forceinline__ EpiSmem epi_stage(const ConvKernelParams &p, float *base, int cpad, int tid) {
   EpiSmem e;
   e.bias = base;
+  e.cpad = cpad;
   for (int c = tid; c < cpad; c += 256) base[c] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
 #pragma unroll
   for (int o = 0; o < kMaxOut; ++o) {
     float *dst = base + (1 + o) * cpad;
-    e.slope[o] = dst;
     if (o < p.n_out && p.out[o].slope)
       for (int c = tid; c < cpad; c += 256) dst[c] = c < p.Cout ? __ldg(p.out[o].slope + c) : 1.f;
   }
@@ -238,24 +238,18 @@ __device__ __forceinline__ EpiSmem epi_stage(const ConvKernelParams &p, float *b
 
 struct EpiPixel {
   bool inside;
+  long pix;               // index of this thread's output pixel in [N, Ho, Wo]
   const float *res;
-  float *dst[kMaxOut];
   float ratio, um;        // partial-conv scalars of this pixel (1, 1 for a dense convolution)
-  float mul[kMaxOut];     // trailing per-pixel factor of each output (1 = none)
 };
 
 __device__ __forceinline__ EpiPixel epi_pixel(const ConvKernelParams &p, int img, int oy, int ox) {
   EpiPixel e;
   e.inside = (oy < p.Ho) & (ox < p.Wo);
-  const long pix = e.inside ? ((long)img * p.Ho + oy) * p.Wo + ox : 0;
-  e.res = p.res ? p.res + pix * p.res_stride : nullptr;
-  e.ratio = p.pc_ratio ? __ldg(p.pc_ratio + pix) : 1.f;      // requested here, consumed after the accumulator barrier
-  e.um = p.pc_um ? __ldg(p.pc_um + pix) : 1.f;
-#pragma unroll
-  for (int o = 0; o < kMaxOut; ++o) {
-    e.dst[o] = o < p.n_out ? p.out[o].ptr + pix * p.out[o].stride : nullptr;
-    e.mul[o] = (o < p.n_out && p.out[o].mul) ? __ldg(p.out[o].mul + pix) : 1.f;
-  }
+  e.pix = e.inside ? ((long)img * p.Ho + oy) * p.Wo + ox : 0;
+  e.res = p.res ? p.res + e.pix * p.res_stride : nullptr;
+  e.ratio = p.pc_ratio ? __ldg(p.pc_ratio + e.pix) : 1.f;      // requested here, consumed after the accumulator barrier
+  e.um = p.pc_um ? __ldg(p.pc_um + e.pix) : 1.f;
   return e;
 }
 
@@ -268,6 +262,10 @@ __device__ __forceinline__ void epi_load_res(const ConvKernelParams &p, const Ep
 }
 
 // The residual of the FIRST chunk must already be in rr (epi_load_res before the accumulator barrier).
+// Structure: the 16 accumulator values of a chunk are finished once (bias, partial-conv renormalisation, residual), then a
+// ROLLED loop runs over the n_out outputs.  With the outputs unrolled the compiler predicated the code of all three instead
+// of branching around the absent ones, and the eight epilogue warps issued ~800 instructions per tile -- after the MMA issue
+// loop was fixed THEY were what the tensor pipe waited for (profiles/ncu_conv_r01q_0).
 __device__ __forceinline__ void epilogue_rows(const ConvKernelParams &p, const EpiSmem &es, const EpiPixel &px, uint32_t taddr,
                                               int n0, int half, float4 (&rr)[4]) {
   for (int c0 = 16 * half; c0 < p.Npad; c0 += 32) {
@@ -282,6 +280,109 @@ __device__ __forceinline__ void epilogue_rows(const ConvKernelParams &p, const E
     float4 rnext[4];
     const bool more = (c0 + 32 < p.Npad) && (n0 + c0 + 32 < p.Cout4);
     if (more) epi_load_res(p, px, n0 + c0 + 32, rnext);
+    float4 bs[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) bs[g] = *reinterpret_cast<const float4 *>(es.bias + n0 + c0 + 4 * g);
+    tmem_ld_wait(raw);
+    if (px.inside) {
+      float4 a[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        a[g] = make_float4(__uint_as_float(raw[4 * g]) + bs[g].x, __uint_as_float(raw[4 * g + 1]) + bs[g].y,
+                           __uint_as_float(raw[4 * g + 2]) + bs[g].z, __uint_as_float(raw[4 * g + 3]) + bs[g].w);
+      }
+      if (p.pc_ratio) {
+        // output = ((raw_out - bias) * mask_ratio + bias) * update_mask, utils/partial_conv.py:74-77, same operation order
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          a[g].x = __fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(a[g].x, bs[g].x), px.ratio), bs[g].x), px.um);
+          a[g].y = __fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(a[g].y, bs[g].y), px.ratio), bs[g].y), px.um);
+          a[g].z = __fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(a[g].z, bs[g].z), px.ratio), bs[g].z), px.um);
+          a[g].w = __fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(a[g].w, bs[g].w), px.ratio), bs[g].w), px.um);
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        a[g].x += rr[g].x; a[g].y += rr[g].y; a[g].z += rr[g].z; a[g].w += rr[g].w;
+      }
+      const int ngroups = min(4, (p.Cout4 - (n0 + c0)) >> 2);      // float4 groups of this chunk that exist in the outputs
+#pragma unroll 1
+      for (int o = 0; o < p.n_out; ++o) {
+        const ConvOut &out = p.out[o];
+        float *dst = out.ptr + px.pix * out.stride + n0 + c0;
+        const float *slope = out.slope ? es.bias + (1 + o) * es.cpad + n0 + c0 : nullptr;
+        const float m = out.mul ? __ldg(out.mul + px.pix) : 1.f;
+        const bool rnd = out.round_tf32 != 0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g >= ngroups) break;
+          float4 w = a[g];
+          if (slope) {
+            const float4 sl = *reinterpret_cast<const float4 *>(slope + 4 * g);
+            w.x = prelu1(w.x, sl.x); w.y = prelu1(w.y, sl.y); w.z = prelu1(w.z, sl.z); w.w = prelu1(w.w, sl.w);
+          }
+          if (out.mul) { w.x *= m; w.y *= m; w.z *= m; w.w *= m; }
+          if (rnd) { w.x = round_tf32(w.x); w.y = round_tf32(w.y); w.z = round_tf32(w.z); w.w = round_tf32(w.w); }
+          if (!(p.debug & 1)) *reinterpret_cast<float4 *>(dst + 4 * g) = w;
+        }
+      }
+    }
+    if (more) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) rr[g] = rnext[g];
+    }
+  }
+}
+
+// ---- the same epilogue with the outputs UNROLLED, for the per-tap kernel: it is not persistent and runs two CTAs per SM,
+// which the register budget of this form (96) allows and that of the rolled form (115) does not; there the epilogue is a
+// tail of each CTA, not a steady-state stage, and fewer registers win.
+struct EpiPixelU {
+  bool inside;
+  const float *res;
+  float *dst[kMaxOut];
+  float ratio, um;        // partial-conv scalars of this pixel (1, 1 for a dense convolution)
+  float mul[kMaxOut];     // trailing per-pixel factor of each output (1 = none)
+};
+
+__device__ __forceinline__ EpiPixelU epi_pixel_u(const ConvKernelParams &p, int img, int oy, int ox) {
+  EpiPixelU e;
+  e.inside = (oy < p.Ho) & (ox < p.Wo);
+  const long pix = e.inside ? ((long)img * p.Ho + oy) * p.Wo + ox : 0;
+  e.res = p.res ? p.res + pix * p.res_stride : nullptr;
+  e.ratio = p.pc_ratio ? __ldg(p.pc_ratio + pix) : 1.f;      // requested here, consumed after the accumulator barrier
+  e.um = p.pc_um ? __ldg(p.pc_um + pix) : 1.f;
+#pragma unroll
+  for (int o = 0; o < kMaxOut; ++o) {
+    e.dst[o] = o < p.n_out ? p.out[o].ptr + pix * p.out[o].stride : nullptr;
+    e.mul[o] = (o < p.n_out && p.out[o].mul) ? __ldg(p.out[o].mul + pix) : 1.f;
+  }
+  return e;
+}
+
+__device__ __forceinline__ void epi_load_res_u(const ConvKernelParams &p, const EpiPixelU &px, int c, float4 (&rr)[4]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    rr[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (px.res && px.inside && c + 4 * g < p.Cout4) rr[g] = *reinterpret_cast<const float4 *>(px.res + c + 4 * g);
+  }
+}
+
+// The residual of the FIRST chunk must already be in rr (epi_load_res before the accumulator barrier).
+__device__ __forceinline__ void epilogue_rows_u(const ConvKernelParams &p, const EpiSmem &es, const EpiPixelU &px, uint32_t taddr,
+                                              int n0, int half, float4 (&rr)[4]) {
+  for (int c0 = 16 * half; c0 < p.Npad; c0 += 32) {
+    if (n0 + c0 >= p.Cout4) break;           // warp-uniform
+    uint32_t raw[16];
+    if (p.debug & 8) {   // experiment: no TMEM reads
+#pragma unroll
+      for (int i = 0; i < 16; ++i) raw[i] = 0;
+    } else {
+      tmem_ld16_issue(taddr + (uint32_t)c0, raw);
+    }
+    float4 rnext[4];
+    const bool more = (c0 + 32 < p.Npad) && (n0 + c0 + 32 < p.Cout4);
+    if (more) epi_load_res_u(p, px, n0 + c0 + 32, rnext);
     float4 bs[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) bs[g] = *reinterpret_cast<const float4 *>(es.bias + n0 + c0 + 4 * g);
@@ -307,7 +408,7 @@ __device__ __forceinline__ void epilogue_rows(const ConvKernelParams &p, const E
           if (o >= p.n_out) break;
           float4 w = a;
           if (p.out[o].slope) {
-            const float4 sl = *reinterpret_cast<const float4 *>(es.slope[o] + c);
+            const float4 sl = *reinterpret_cast<const float4 *>(es.bias + (1 + o) * es.cpad + c);
             w.x = prelu1(w.x, sl.x); w.y = prelu1(w.y, sl.y); w.z = prelu1(w.z, sl.z); w.w = prelu1(w.w, sl.w);
           }
           if (p.out[o].mul) {
@@ -327,7 +428,9 @@ __device__ __forceinline__ void epilogue_rows(const ConvKernelParams &p, const E
   }
 }
 
-__global__ void __launch_bounds__(kConvThreads) k_conv_tf32(const __grid_constant__ CUtensorMap map_a,
+
+// two CTAs per SM: the per-tap kernel is not persistent, one CTA's epilogue overlaps the other's main loop
+__global__ void __launch_bounds__(kConvThreads, 2) k_conv_tf32(const __grid_constant__ CUtensorMap map_a,
                                                             const __grid_constant__ CUtensorMap map_b,
                                                             const ConvKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -425,12 +528,12 @@ __global__ void __launch_bounds__(kConvThreads) k_conv_tf32(const __grid_constan
     const int m = q * 32 + lane;               // accumulator row = pixel of the tile
     const int py = m / p.tile_w, px = m - py * p.tile_w;
     const EpiSmem es = epi_stage(p, epi_tab, p.cpad, threadIdx.x - 64);
-    const EpiPixel ep = epi_pixel(p, img, y0 + py, x0 + px);
+    const EpiPixelU ep = epi_pixel_u(p, img, y0 + py, x0 + px);
     float4 rr[4];
-    epi_load_res(p, ep, n0 + 16 * half, rr);
+    epi_load_res_u(p, ep, n0 + 16 * half, rr);
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    epilogue_rows(p, es, ep, tmem_base + ((uint32_t)(q * 32) << 16), n0, half, rr);
+    epilogue_rows_u(p, es, ep, tmem_base + ((uint32_t)(q * 32) << 16), n0, half, rr);
   }
   tc_fence_before();
   __syncthreads();
@@ -924,12 +1027,10 @@ static int make_act_map(EncodeTiledFn enc, const kb_conv_args *a, int box_w, int
                            (cuuint64_t)a->x_stride * 4 * a->W * a->H};
   cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-  static const int promo = env_int("KB_TMA_PROMO", 2);
-  const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
-                                    : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-                                    : promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+  // (L2 promotion NONE / 64B / 128B / 256B measure the same here)
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(a->x), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("kb_conv2d: cuTensorMapEncodeTiled(activations) failed with CUresult %d", (int)r);
     return KB_EINVAL;

@@ -1,3 +1,7 @@
-for e in 0 1 2 7; do KB_ACCUM_EXP=$e python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-full-pipeline | python -c "
+python -m pytest tests/test_gpu_conv.py -x -q 2>&1 | tail -3
+python tools/bench_conv.py --no-cudnn --nets | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('exp', $e, {k:round(v,4) for k,v in d['stage_ms_per_launch'].items() if k in ('splat_accum','resolve','memset_accum')})"; done
+for l in sys.stdin:
+    d=json.loads(l)
+    if 'case' in d: print(d['case'], round(d['ms']*1000,1), round(d['frac_tf32_peak'],3))
+    else: print(d['net'], round(d['ms'],3))"

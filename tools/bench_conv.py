@@ -90,19 +90,19 @@ def main():
         data = torch.randn(1, 68, H, W, device=dev)
         mask = (torch.rand(1, 1, H, W, device=dev) > 0.2).float()
         net.normalize_images_disp(torch.rand(1, 3, H, W, device=dev), torch.rand(1, 1, H, W, device=dev), True)
-        ms = timed(lambda: net(mask, tensorData=data), 5, 2)
+        ms = timed(lambda: net(mask, tensorData=data), 5, 4)
         print(json.dumps({"net": "Inpaint.forward 1024x768", "ms": ms, "tflops": 819.5 / ms, "frac_tf32_peak": 819.5 / ms / TF32_PEAK}))
         ref = kb_helpers.deterministic_state(Refine().eval()).to(dev)
         img, dlo = torch.rand(1, 3, H, W, device=dev), torch.rand(1, 1, H // 4, W // 4, device=dev)
-        ms = timed(lambda: ref(img, dlo), 5, 2)
+        ms = timed(lambda: ref(img, dlo), 5, 4)
         print(json.dumps({"net": "Refine.forward 1024x768", "ms": ms, "tflops": 311.3 / ms, "frac_tf32_peak": 311.3 / ms / TF32_PEAK}))
         sem = kb_helpers.deterministic_state(Semantics().eval()).to(dev)
         dis = kb_helpers.deterministic_state(Disparity().eval()).to(dev)
         small = torch.rand(1, 3, H // 2, W // 2, device=dev)
         s = sem(small)
-        ms = timed(lambda: sem(small), 5, 2)
+        ms = timed(lambda: sem(small), 5, 4)
         print(json.dumps({"net": "Semantics.forward 512x384", "ms": ms, "tflops": 138.4 / ms, "frac_tf32_peak": 138.4 / ms / TF32_PEAK}))
-        ms = timed(lambda: dis(small, s), 5, 2)
+        ms = timed(lambda: dis(small, s), 5, 4)
         print(json.dumps({"net": "Disparity.forward 512x384", "ms": ms, "tflops": 87.7 / ms, "frac_tf32_peak": 87.7 / ms / TF32_PEAK}))
 
 
