@@ -192,6 +192,7 @@ struct ConvKernelParams {
   int pitch;            // halo row pitch in pixels (>= tile_w + ksize - 1)
   int a_stage_bytes;    // one halo slice (32 channels), rounded up to 1024
   int a_stages, b_stages;
+  int acc_stages;       // accumulator ring depth in TMEM (2..kAccMax)
   int epi_off;          // byte offset of the epilogue tables from the aligned shared-memory base
   int resident;         // all weight panels stay in shared memory for the life of the CTA
   int n_blocks;
@@ -550,6 +551,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) k_conv_tf32(const __grid_cons
 // tile.  CTAs are persistent: the TMA producer runs ahead across tiles, the accumulator is double-buffered in TMEM so the
 // epilogue of tile i overlaps the MMAs of tile i+1, and filters small enough stay resident in shared memory.
 constexpr int kHaloTileW = 8, kHaloTileH = 16;
+constexpr int kAccMax = 4;   // accumulator ring in TMEM: up to 4 tiles between the MMA issuer and the epilogue
 
 // Work item w = ((img * tiles_y + ty) * tiles_x + tx) * n_blocks + nb, visited as w = blockIdx.x, += gridDim.x, ...
 // The coordinates are carried along as mixed-radix digits: the 64-bit divisions of a direct decomposition cost each of
@@ -609,8 +611,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
   uint64_t *b_full = a_empty + p.a_stages;
   uint64_t *b_empty = b_full + p.b_stages;
   uint64_t *acc_full = b_empty + p.b_stages;
-  uint64_t *acc_empty = acc_full + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+  uint64_t *acc_empty = acc_full + kAccMax;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + kAccMax);
   float *epi_tab = reinterpret_cast<float *>(smem + p.epi_off);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -621,7 +623,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 8); }
+    for (int s = 0; s < kAccMax; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 8); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -715,8 +717,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
           if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; a_lo = a_base_lo; }
         }
         if (leader) umma_commit(acc_full + as);
-        as ^= 1u;
-        if (as == 0) phacc ^= 1u;
+        if (++as == (uint32_t)p.acc_stages) { as = 0; phacc ^= 1u; }
       }
     } else {
       for (int item = 0; item < n_items; ++item) {
@@ -749,8 +750,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
           if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; a_lo = a_base_lo; }
         }
         if (leader) umma_commit(acc_full + as);
-        as ^= 1u;
-        if (as == 0) phacc ^= 1u;
+        if (++as == (uint32_t)p.acc_stages) { as = 0; phacc ^= 1u; }
       }
     }
   } else {
@@ -772,8 +772,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
-      as ^= 1u;
-      if (as == 0) phacc ^= 1u;
+      if (++as == (uint32_t)p.acc_stages) { as = 0; phacc ^= 1u; }
     }
   }
   tc_fence_before();
@@ -1175,8 +1174,9 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
   p.debug = env_int("KB_CONV_DEBUG", 0);
   const int box_bytes = p.pitch * halo_h * kChunk * 4;
   p.a_stage_bytes = (box_bytes + 1023) & ~1023;
-  p.tmem_cols = (uint32_t)max(32, pow2_at_least(2 * npad));
-  KB_REQUIRE(p.tmem_cols <= 512, "kb_conv2d: accumulator does not fit TMEM");
+  p.acc_stages = min(kAccMax, 512 / npad);
+  KB_REQUIRE(p.acc_stages >= 2, "kb_conv2d: accumulator does not fit TMEM");
+  p.tmem_cols = (uint32_t)max(32, pow2_at_least(p.acc_stages * npad));
   const size_t bar_bytes = 1024;                         // barriers + TMEM slot
   const size_t fixed = 1024 + bar_bytes + epi_bytes;     // alignment slack + barriers + epilogue tables
   const size_t budget = smem_cap - fixed;
@@ -1191,7 +1191,7 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
     KB_REQUIRE(p.b_stages >= 2, "kb_conv2d: weight ring does not fit shared memory");
   }
   if (a->stages > 0) p.a_stages = max(2, min(a->stages, p.a_stages));
-  KB_REQUIRE((2 * p.a_stages + 2 * p.b_stages + 4) * sizeof(uint64_t) + 16 <= bar_bytes, "kb_conv2d: too many pipeline stages");
+  KB_REQUIRE((2 * p.a_stages + 2 * p.b_stages + 2 * kAccMax) * sizeof(uint64_t) + 16 <= bar_bytes, "kb_conv2d: too many pipeline stages");
   p.epi_off = (int)((size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * b_bytes + bar_bytes);
   p.work_items = tiles * n_blocks;
   rc = make_act_map(enc, a, p.pitch, halo_h, 1, &map_a);
