@@ -34,14 +34,19 @@ W, H, FOCAL, BASELINE = 1024, 768, 512.0, 120
 METRIC = "novel-view frames/sec at 1024x768, 150-frame KBE"
 
 
+DOLLY = False
+
+
 def build_workload(frames, world=1, rank=0):
     from ken_burns_effect_b200.utils import common as kb
     from ken_burns_effect_b200.utils import synthetic
+    # dolly mode skips the inpainting passes (utils/common.py:217-218): the cloud is the raw H*W grid and the focal length
+    # changes with every pose (:225-229)
     pts, rgb, dep, common = synthetic.scene_cloud(W, H, seed=1234, focal=FOCAL, baseline=BASELINE,
-                                                  inpaint_standin=True)
-    zoom = synthetic.default_zoom(W, H)
+                                                  inpaint_standin=not DOLLY)
+    zoom = synthetic.default_zoom(W, H, dolly=DOLLY)
     steps = np.linspace(0.0, 1.0, frames * world).tolist()[rank::world]
-    st = {'dblSteps': steps, 'objectFrom': zoom['objectFrom'], 'objectTo': zoom['objectTo'], 'dolly': False}
+    st = {'dblSteps': steps, 'objectFrom': zoom['objectFrom'], 'objectTo': zoom['objectTo'], 'dolly': DOLLY}
     poses = kb.kenburns_poses(st, common)
     cw = max(zoom['objectFrom']['intCropWidth'], zoom['objectTo']['intCropWidth'])
     ch = max(zoom['objectFrom']['intCropHeight'], zoom['objectTo']['intCropHeight'])
@@ -240,13 +245,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-pipeline", action="store_true")
+    ap.add_argument("--dolly", action="store_true", help="BASELINE configs[2]: the dolly-zoom path (per-pose focal length, no inpainted points)")
     ap.add_argument("--size", default="1024x768", help="WxH of the synthetic input (BASELINE configs[3]: 3840x2160 --frames 300)")
     args = ap.parse_args()
-    global W, H, FOCAL, METRIC
+    global W, H, FOCAL, METRIC, DOLLY
+    DOLLY = args.dolly
     W, H = (int(v) for v in args.size.lower().split("x"))
     FOCAL = max(W, H) / 2.0          # dblFocal = max side / 2 like pipeline.py:26 for 1024x768
-    if (W, H) != (1024, 768) or args.frames != 150:
-        METRIC = f"novel-view frames/sec at {W}x{H}, {args.frames}-frame KBE"
+    if (W, H) != (1024, 768) or args.frames != 150 or DOLLY:
+        METRIC = f"novel-view frames/sec at {W}x{H}, {args.frames}-frame KBE" + (" (--dolly)" if DOLLY else "")
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     quiet_stdout()
     if args.impl == "reference":
@@ -382,7 +389,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"kbe {W}x{H} -> {args.frames}-frame 3D KBE (configs[{1 if (W, H) == (1024, 768) else 3}]), per-frame render loop "
+        "config": {"workload": f"kbe {'--dolly ' if DOLLY else ''}{W}x{H} -> {args.frames}-frame 3D KBE (configs[{(2 if DOLLY else 1) if (W, H) == (1024, 768) else 3}]), per-frame render loop "
                                "(process_shift..resize, utils/common.py:222-260)",
                    "frames_per_step_per_gpu": F, "points": N, "pixels": P, "poses_per_launch": renderer.batch,
                    "parallelism": f"frame-shard x{world}" + (" + NCCL broadcast of the cloud per step" if world > 1 else ""),

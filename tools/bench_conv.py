@@ -92,6 +92,13 @@ def main():
         net.normalize_images_disp(torch.rand(1, 3, H, W, device=dev), torch.rand(1, 1, H, W, device=dev), True)
         ms = timed(lambda: net(mask, tensorData=data), 5, 4)
         print(json.dumps({"net": "Inpaint.forward 1024x768", "ms": ms, "tflops": 819.5 / ms, "frac_tf32_peak": 819.5 / ms / TF32_PEAK}))
+        from ken_burns_effect_b200.models.partial_inpainting import Inpaint as PartialInpaint
+        pnet = kb_helpers.deterministic_state(PartialInpaint().eval()).to(dev)
+        pnet.normalize_images_disp(torch.rand(1, 3, H, W, device=dev), torch.rand(1, 1, H, W, device=dev), True)
+        ms = timed(lambda: pnet(mask, tensorData=data), 5, 4)
+        # FLOPs of the data convolutions only: the mask "convolutions" of the reference are a box filter here
+        print(json.dumps({"net": "PartialInpaint.forward 1024x768 (kbe.py --partial-conv)", "ms": ms, "tflops": 819.5 / ms,
+                          "frac_tf32_peak": 819.5 / ms / TF32_PEAK}))
         ref = kb_helpers.deterministic_state(Refine().eval()).to(dev)
         img, dlo = torch.rand(1, 3, H, W, device=dev), torch.rand(1, 1, H // 4, W // 4, device=dev)
         ms = timed(lambda: ref(img, dlo), 5, 4)
