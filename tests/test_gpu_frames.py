@@ -64,6 +64,23 @@ def test_frames_small(W, H, focal, extra, dolly):
     _compare(mine, ref)
 
 
+def test_frames_dolly_dense_holes():
+    """Dolly zoom at a size where the late poses have far more than 16384 holes (the foreground spreads apart): those poses
+    take the thread-per-hole fill kernel (kf_fill_dense), the early ones the warp-per-hole kernel; both must give the
+    oracle's frames."""
+    oracle.set_threads(0)
+    W, H, focal = 512, 384, 256.0
+    pts, rgb, dep, common = helpers.scene(W, H, focal, 0)
+    steps = [0.0, 0.5, 0.8, 1.0]
+    mine, poses, crop = _render_frames(pts, rgb, dep, common, W, H, steps, dolly=True, batch=4)
+    ref = _oracle_frames(pts, rgb, dep, common, W, H, poses, crop)
+    _compare(mine, ref)
+    # the regime really was exercised: count the holes of the last pose with the oracle's own render
+    data = np.concatenate([rgb, dep], 0)
+    r, e = oracle.render_pointcloud(oracle.shift_points(pts, poses[-1][0])[None], data[None], W, H, poses[-1][1], common['dblBaseline'])
+    assert int(((r[0, 3] * (e[0, 0] > 0)) <= 0).sum()) > 16384
+
+
 def test_frames_full_size_two_poses():
     oracle.set_threads(0)
     W, H, focal = 1024, 768, 512.0
