@@ -64,7 +64,7 @@ def main():
         tot = sum(a["stall"].values()) or 1.0
         top = sorted(a["stall"].items(), key=lambda kv: -kv[1])[:3]
         lines.append(f"| {name} | {n} | " + " | ".join(cells) + " | " + ", ".join(f"{k} {100 * v / tot:.0f}%" for k, v in top) + " |")
-        traffic[name] = int((a["vals"].get("DRAM rd MB", 0) + a["vals"].get("DRAM wr MB", 0)) / n * 1e6)
+        traffic[name.split("<")[0]] = int((a["vals"].get("DRAM rd MB", 0) + a["vals"].get("DRAM wr MB", 0)) / n * 1e6)
     with open(out + "_summary.md", "w") as f:
         f.write(f"ncu --set full --clock-control none, per-launch averages; source: {rep}\n\n" + "\n".join(lines) + "\n")
     if "--traffic" in sys.argv:
