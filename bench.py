@@ -190,7 +190,8 @@ def run_reference(args):
     if rank != 0:
         return
     # keep the whole run within a few minutes: ~60 s of CPU work spread over the timed steps
-    per_step = max(1.0, 60.0 / max(1, args.steps))
+    budget = float(os.environ.get("KB_BENCH_CPU_BUDGET_S", "60"))       # seconds of CPU work over the timed steps
+    per_step = max(1.0, budget / max(1, args.steps))
     vals, nframes = [], 0
     for i in range(args.warmup + args.steps):
         fps, cores, dt, n = cpu_baseline(budget_s=per_step if i >= args.warmup else 1.0, max_frames=150)

@@ -1,12 +1,12 @@
 """CPU oracle for the novel-view render path -- TEST INFRASTRUCTURE, not product code.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs import this
-package.  The product package (ken_burns_effect_b200) must never import it; tests/test_no_oracle_in_product.py
+package.  The product package (ken_burns_effect_b200) must never import it; tests/test_abi.py::test_product_never_touches_the_oracle
 greps for that.
 
 `kb_oracle.c` restates the reference's CUDA kernels (utils/common.py:428-937) and its numpy/OpenCV frame
 tail (utils/common.py:255-257) in plain C; this module is the numpy/ctypes face of it.  Parity is pinned
-against the reference's own kernels compiled by build_ref.py (see tests/test_gpu_reference_pin.py and the
+against the reference's own kernels compiled by build_ref.py (see tests/test_gpu_render.py, tests/test_gpu_mask.py and the
 fixtures in tests/golden/).
 """
 import ctypes

@@ -10,7 +10,7 @@
  * contracts a*b+c into one FMA (checked in the SASS of the reference cubins built by oracle/build_ref.py).
  * Compile with -ffp-contract=off so the C compiler adds no contraction of its own (see Makefile).
  *
- * Parity pin: tests/test_gpu_reference_pin.py runs the reference's own kernels (oracle/_ref/ cubins) on
+ * Parity pin: tests/test_gpu_render.py and tests/test_gpu_mask.py run the reference's own kernels (oracle/_ref/ cubins) on
  * the B200 and compares them with this file bit-for-bit (z-buffer) / to fp32 summation-order noise
  * (accumulators); tests/golden/ holds outputs of those reference kernels for the CPU-only suite.
  *
