@@ -76,6 +76,18 @@ int kb_splat_accum(const float *xyz, const float *data, int B, long N, int C, co
 int kb_normalize(const float *accum, int B, int C, int H, int W, float *render, float *existing,
                  kb_stream_t stream);
 
+/* The same accumulation with the per-point data as ROWS: data_rows[(b*N + n) * row_stride + c], channels contiguous (the NHWC
+ * layout kb_conv2d writes), so features go from a convolution epilogue into the splat without a layout change
+ * (models/pointcloud_inpainting.py:199-206). */
+int kb_splat_accum_rows(const float *xyz, const float *data_rows, long row_stride, int B, long N, int C, const float *shift_host,
+                        double focal, double baseline, const float *zee, float *accum, int H, int W, kb_stream_t stream);
+/* weight[B,1,H,W] = accum[..., C]  (tensorExisting of utils/common.py:686, before thresholding). */
+int kb_accum_weight(const float *accum, int B, int C, int H, int W, float *weight, kb_stream_t stream);
+/* In place: accum[..., c] = accum[..., c] / (accum[..., C] + 1e-7) * mask for c < C, then accum[..., C] = mask (mask [B,H,W],
+ * NULL = ones): utils/common.py:686 followed by `render * existing` and torch.cat([data, mask]) of
+ * models/pointcloud_inpainting.py:210, :135 -- the accumulator becomes the NHWC input of the inpainting GridNet. */
+int kb_normalize_rows(float *accum, int B, int C, int H, int W, const float *mask, kb_stream_t stream);
+
 /* The whole of render_pointcloud (four launches above).  workspace: kb_render_workspace_bytes() bytes. */
 size_t kb_render_workspace_bytes(int B, int C, int H, int W);
 int kb_render_pointcloud(const float *xyz, const float *data, int B, long N, int C, int W, int H,

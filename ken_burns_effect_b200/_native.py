@@ -50,6 +50,10 @@ SIGNATURES = {
     "kb_accum_channels": (c_int, [c_int]),
     "kb_splat_accum": (c_int, [c_void, c_void, c_int, c_long, c_int, c_f32p, c_double, c_double, c_void, c_void,
                                c_int, c_int, c_void]),
+    "kb_splat_accum_rows": (c_int, [c_void, c_void, c_long, c_int, c_long, c_int, c_f32p, c_double, c_double, c_void, c_void,
+                                    c_int, c_int, c_void]),
+    "kb_accum_weight": (c_int, [c_void, c_int, c_int, c_int, c_int, c_void, c_void]),
+    "kb_normalize_rows": (c_int, [c_void, c_int, c_int, c_int, c_int, c_void, c_void]),
     "kb_normalize": (c_int, [c_void, c_int, c_int, c_int, c_int, c_void, c_void, c_void]),
     "kb_render_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "kb_render_pointcloud": (c_int, [c_void, c_void, c_int, c_long, c_int, c_int, c_int, c_double, c_double,

@@ -172,6 +172,93 @@ __global__ void __launch_bounds__(256) k_splat_accum(const float *__restrict__ x
   }
 }
 
+
+// updateOutput with the per-point data given as ROWS (point-major, `rs` floats per point, channels contiguous): the layout the
+// convolutions produce (NHWC), so that the 64 context features of pointcloud_inpainting (:199-206) go from the conv epilogue
+// into the splat without the NHWC -> NCHW -> torch.cat round trip (0.26 ms and 430 MB of temporaries per inpainting pass).
+__global__ void __launch_bounds__(256) k_splat_accum_rows(const float *__restrict__ xyz, const float *__restrict__ rows, long rs,
+                                                          long N, int C, int Cp, Shift3 sh, Camera cam,
+                                                          const float *__restrict__ zee, float *__restrict__ accum) {
+  const int b = blockIdx.y;
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float *s = xyz + (long)b * 3 * N;
+  float x = __ldg(s + n), y = __ldg(s + N + n), z = __ldg(s + 2 * N + n);
+  if (sh.on) shift_point(x, y, z, sh.x, sh.y, sh.z);
+  Proj p;
+  if (!project(x, y, z, cam, p)) return;
+  const long P = (long)cam.H * cam.W;
+  const float *zb = zee + (long)b * P;
+  float w[4] = {p.wnw, p.wne, p.wsw, p.wse};
+  long pix[4];
+  bool on[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int px = p.nwx + (k & 1), py = p.nwy + (k >> 1);
+    on[k] = (px >= 0) & (px < cam.W) & (py >= 0) & (py < cam.H);
+    pix[k] = on[k] ? (long)py * cam.W + px : 0;
+    if (on[k]) on[k] = z_gate(p.err, __ldg(zb + pix[k]));
+    if (on[k]) on[k] = (w[k] != 0.0f);
+  }
+  if (!(on[0] | on[1] | on[2] | on[3])) return;
+  const float *d = rows + ((long)b * N + n) * rs;
+  float *ab = accum + (long)b * P * Cp;
+  for (int c0 = 0; c0 < Cp; c0 += 4) {
+    float v[4];
+    if (c0 + 4 <= C) {
+      const float4 t = __ldg(reinterpret_cast<const float4 *>(d + c0));
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + j;
+        v[j] = (c < C) ? __ldg(d + c) : (c == C ? 1.0f : 0.0f);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!on[k]) continue;
+      red_add_v4(ab + pix[k] * Cp + c0, __fmul_rn(v[0], w[k]), __fmul_rn(v[1], w[k]), __fmul_rn(v[2], w[k]), __fmul_rn(v[3], w[k]));
+    }
+  }
+}
+
+// The weight channel of channels-last accumulators as a [B,1,H,W] map (tensorExisting of :686 before any thresholding).
+__global__ void __launch_bounds__(256) k_accum_weight(const float *__restrict__ accum, int C, int Cp, long total, float *__restrict__ w) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) w[i] = accum[i * Cp + C];
+}
+
+// In place: accum[p][c] = accum[p][c] / (accum[p][C] + 1e-7) * mask[p] for c < C (:686 and `render * existing`,
+// pointcloud_inpainting.py:210), then accum[p][C] = mask[p] -- the rows become the network input cat([data, mask]) (:135).
+__global__ void __launch_bounds__(256) k_normalize_rows(float *__restrict__ accum, int C, int Cp, long total, const float *__restrict__ mask) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;     // one thread per (pixel, group of 4 channels)
+  const int groups = Cp / 4;
+  const long pix = i / groups;
+  const int c0 = (int)(i - pix * groups) * 4;
+  if (pix >= total) return;
+  float *row = accum + pix * Cp;
+  const float den = __fadd_rn(row[C], 0.0000001f);
+  const float m = mask ? mask[pix] : 1.0f;
+  float4 v = *reinterpret_cast<float4 *>(row + c0);
+  float a[4] = {v.x, v.y, v.z, v.w};
+  // the group that holds channel C writes the weight back unchanged, so the other groups of the pixel may read it at any
+  // time; the mask replaces it in a second launch (kb_normalize_rows)
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + j;
+    if (c < C) a[j] = __fmul_rn(__fdiv_rn(a[j], den), m);
+  }
+  *reinterpret_cast<float4 *>(row + c0) = make_float4(a[0], a[1], a[2], a[3]);
+}
+__global__ void __launch_bounds__(256) k_set_mask_channel(float *__restrict__ accum, int C, int Cp, long total, const float *__restrict__ mask) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float *row = accum + i * Cp;
+  row[C] = mask ? mask[i] : 1.0f;
+  for (int c = C + 1; c < Cp; ++c) row[c] = 0.0f;
+}
+
 // epilogue :686 -- channels-last accumulators -> NCHW render + existing.  A CTA handles 32 pixels x all
 // channels through shared memory so that both the channels-last reads and the planar writes coalesce.
 __global__ void __launch_bounds__(256) k_normalize(const float *__restrict__ accum, int C, int Cp, long P,
@@ -480,6 +567,45 @@ int kb_splat_accum(const float *xyz, const float *data, int B, long N, int C, co
                                       zee, accum);
   count_launch(2);
   return check_launch("kb_splat_accum");
+}
+
+int kb_splat_accum_rows(const float *xyz, const float *data_rows, long row_stride, int B, long N, int C, const float *shift_host,
+                        double focal, double baseline, const float *zee, float *accum, int H, int W, kb_stream_t stream) {
+  KB_REQUIRE(xyz && data_rows && zee && accum && B > 0 && N > 0 && C > 0 && H > 0 && W > 0, "kb_splat_accum_rows: bad arguments");
+  KB_REQUIRE(row_stride >= C && row_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(data_rows) & 15) == 0,
+             "kb_splat_accum_rows: rows must be 16-byte aligned with a stride that is a multiple of 4 floats and >= C");
+  KB_REQUIRE((long)H * W < (1L << 31) && H <= KB_MAX_SIDE && W <= KB_MAX_SIDE, "kb_splat_accum_rows: image too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Cp = kb_accum_channels(C);
+  cudaError_t e = cudaMemsetAsync(accum, 0, sizeof(float) * (size_t)B * H * W * Cp, st);
+  if (e != cudaSuccess) {
+    set_error("kb_splat_accum_rows memset: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  dim3 grid(cdiv(N, 256), B);
+  k_splat_accum_rows<<<grid, 256, 0, st>>>(xyz, data_rows, row_stride, N, C, Cp, make_shift(shift_host),
+                                           make_camera(focal, baseline, H, W), zee, accum);
+  count_launch(2);
+  return check_launch("kb_splat_accum_rows");
+}
+
+int kb_accum_weight(const float *accum, int B, int C, int H, int W, float *weight, kb_stream_t stream) {
+  KB_REQUIRE(accum && weight && B > 0 && C > 0 && H > 0 && W > 0, "kb_accum_weight: bad arguments");
+  const long total = (long)B * H * W;
+  k_accum_weight<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(accum, C, kb_accum_channels(C), total, weight);
+  count_launch();
+  return check_launch("kb_accum_weight");
+}
+
+int kb_normalize_rows(float *accum, int B, int C, int H, int W, const float *mask, kb_stream_t stream) {
+  KB_REQUIRE(accum && B > 0 && C > 0 && H > 0 && W > 0, "kb_normalize_rows: bad arguments");
+  const int Cp = kb_accum_channels(C);
+  const long total = (long)B * H * W;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_normalize_rows<<<cdiv(total * (Cp / 4), 256), 256, 0, st>>>(accum, C, Cp, total, mask);
+  k_set_mask_channel<<<cdiv(total, 256), 256, 0, st>>>(accum, C, Cp, total, mask);   // after every group has read the weight
+  count_launch(2);
+  return check_launch("kb_normalize_rows");
 }
 
 int kb_normalize(const float *accum, int B, int C, int H, int W, float *render, float *existing,

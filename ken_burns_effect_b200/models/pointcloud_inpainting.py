@@ -76,9 +76,31 @@ class Inpaint(nn.Module):
         buf = torch.empty(N, H, W, cs.round4(C + 1), device=tensorData.device, dtype=torch.float32)
         cs.to_nhwc(tensorData, dst=buf[..., :C])                       # torch.cat([tensorData, tensorMasks], 1), :135
         cs.to_nhwc(tensorMasks, dst=buf[..., C:C + 1])
-        x = buf[..., :C + 1]
+        return self._grid_rows_b200(buf)
+
+    def _grid_rows_b200(self, buf):
+        """The GridNet + heads on an NHWC input buffer [N,H,W,72] whose channels 0..68 are cat([data, mask])."""
+        x = buf[..., :69]
         row0 = cs.grid_forward_nhwc(self, self.FEATURES, lambda outs: cs.run_block(self.moduleInput, x, outs, x_raw=x))
         return cs.to_nchw(cs.head_nhwc(self.moduleImage, row0)), cs.to_nchw(cs.head_nhwc(self.moduleDisparity, row0))
+
+    def _render_rows_b200(self, img, disp, points_shifted, objectCommon, dblFocal):
+        """Context features -> 68-channel splat -> mask -> normalised, masked network input, all in NHWC: the context
+        convolution writes next to image and disparity in one [1,H,W,68] buffer of per-point rows, the splat reads those rows,
+        and its accumulators are normalised in place into the [1,H,W,72] buffer the GridNet reads (:199-210, :135).
+        -> (buf, existing [1,1,H,W])."""
+        _, _, H, W = img.shape
+        rows = torch.empty(1, H, W, 68, device=img.device, dtype=torch.float32)
+        cs.to_nhwc(torch.cat([img, disp], 1), dst=rows[..., 0:4])
+        c0, a0, c1, a1 = list(self.moduleContext)
+        t, = cs.conv2d(rows[..., 0:4], cs.packed(c0), [(a0.weight, True, None)])
+        cs.conv2d(t, cs.packed(c1), [(a1.weight, False, rows[..., 4:68])])
+        acc, weight = kb.render_rows(points_shifted, rows.view(1, H * W, 68), objectCommon['intWidth'], objectCommon['intHeight'],
+                                     dblFocal, objectCommon['dblBaseline'])
+        existing = (weight > 0.0).float()
+        existing = existing * kb.spatial_filter(existing, 'median-5')
+        kb.normalize_rows(acc, 68, existing)
+        return acc, existing
 
     def _context(self, img, disp):
         return cs.graphed(self, 'context', self._context_b200, img.contiguous(), disp.contiguous())
@@ -109,5 +131,27 @@ class Inpaint(nn.Module):
         return render * existing, existing
 
     def pointcloud_inpainting(self, tensorImage, tensorDisparity, tensorShift, objectCommon, dblFocal=None):
+        if tensorImage.is_cuda and type(self).forward is Inpaint.forward and \
+                (objectCommon['intHeight'], objectCommon['intWidth']) == tuple(tensorImage.shape[2:]):
+            return self._pointcloud_inpainting_b200(tensorImage, tensorDisparity, tensorShift, objectCommon, dblFocal)
         render, existing = self._render_inputs(tensorImage, tensorDisparity, tensorShift, objectCommon, dblFocal)
         return self.forward(tensorData=render, tensorMasks=existing)
+
+    def _pointcloud_inpainting_b200(self, tensorImage, tensorDisparity, tensorShift, objectCommon, dblFocal):
+        """pointcloud_inpainting (:185-213) without leaving the NHWC layout between the context convolutions, the splat and
+        the GridNet; same arithmetic as _render_inputs() + forward(tensorData=, tensorMasks=)."""
+        if dblFocal is None:
+            dblFocal = objectCommon['dblFocal']
+        assert tensorImage.shape[0] == 1, 'Please process one image at a time.'
+        depth = (dblFocal * objectCommon['dblBaseline']) / (tensorDisparity + 0.0000001)
+        valid = (kb.spatial_filter(tensorDisparity / tensorDisparity.max(), 'laplacian').abs() < 0.03).float()
+        points = kb.depth_to_points(depth * valid, dblFocal).view(1, 3, -1)
+        img, disp = self.normalize_images_disp(tensorImage, tensorDisparity, not_normed=True)
+        buf, existing = self._render_rows_b200(img, disp, points + tensorShift, objectCommon, dblFocal)
+        oimg, odisp = cs.graphed(self, 'grid_rows', self._grid_rows_b200, buf)
+        oimg, odisp = self.normalize_images_disp(oimg, odisp, not_normed=False)
+        return {
+            'tensorExisting': existing,
+            'tensorImage': oimg.clamp(0.0, 1.0) if self.training == False else oimg,  # noqa: E712
+            'tensorDisparity': F.threshold(input=odisp, threshold=0.0, value=0.0),
+        }

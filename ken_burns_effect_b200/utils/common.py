@@ -127,6 +127,38 @@ def render_pointcloud(tensorInput, tensorData, intWidth, intHeight, dblFocal, db
     return render, existing
 
 
+def render_rows(tensorInput, data_rows, intWidth, intHeight, dblFocal, dblBaseline):
+    """render_pointcloud (utils/common.py:428-686) for per-point data given as NHWC rows [B, N, C] (a view whose last stride is
+    1 and whose row stride is a multiple of 4 floats).  Returns (accum [B,H,W,Cp] channels-last accumulators with the weight in
+    channel C, weight [B,1,H,W]); kb_normalize_rows / normalize_rows() finishes them in place."""
+    _need_cuda(tensorInput, data_rows)
+    pts = tensorInput.contiguous()
+    B, N, C = data_rows.shape
+    if pts.shape != (B, 3, N) or data_rows.stride(2) != 1 or data_rows.stride(1) % 4 or data_rows.stride(0) != N * data_rows.stride(1):
+        raise RuntimeError(f"render_rows: points {tuple(pts.shape)} / rows {tuple(data_rows.shape)} strides {data_rows.stride()}")
+    H, W = int(intHeight), int(intWidth)
+    L = nat.lib()
+    P = H * W
+    zz = torch.empty(2, B, H, W, device=pts.device, dtype=torch.float32)
+    nat.check(L.kb_splat_min(_ptr(pts), B, N, None, float(dblFocal), float(dblBaseline), _ptr(zz[0]), H, W, None, _stream()), "kb_splat_min")
+    nat.check(L.kb_degrid(_ptr(zz[0]), _ptr(zz[1]), B, H, W, _stream()), "kb_degrid")
+    Cp = L.kb_accum_channels(C)
+    acc = torch.empty(B, H, W, Cp, device=pts.device, dtype=torch.float32)
+    nat.check(L.kb_splat_accum_rows(_ptr(pts), _ptr(data_rows), data_rows.stride(1), B, N, C, None, float(dblFocal),
+                                    float(dblBaseline), _ptr(zz[1]), _ptr(acc), H, W, _stream()), "kb_splat_accum_rows")
+    weight = torch.empty(B, 1, H, W, device=pts.device, dtype=torch.float32)
+    nat.check(L.kb_accum_weight(_ptr(acc), B, C, H, W, _ptr(weight), _stream()), "kb_accum_weight")
+    return acc, weight
+
+
+def normalize_rows(acc, C, mask):
+    """In place: acc[..., :C] = acc[..., :C] / (acc[..., C] + 1e-7) * mask, acc[..., C] = mask  (mask [B,1,H,W] or [B,H,W])."""
+    B, H, W, _ = acc.shape
+    m = mask.reshape(B, H, W).contiguous()
+    nat.check(nat.lib().kb_normalize_rows(_ptr(acc), B, C, H, W, _ptr(m), _stream()), "kb_normalize_rows")
+    return acc
+
+
 def accumulate_with_zee(tensorInput, tensorData, tensorZee, dblFocal, dblBaseline):
     """Passes 3+4 of render_pointcloud (updateOutput + epilogue, utils/common.py:585-686) against a z-buffer
     supplied by the caller ([B,1,H,W], already degridded).  Lets a test isolate the accumulation from the

@@ -90,3 +90,38 @@ def test_pointcloud_inpainting_render_inputs_vs_oracle():
     o_mask = o_mask * oracle.median5_binary(o_mask)
     assert np.array_equal(existing.cpu().numpy(), o_mask)
     assert kb_helpers.rel_l2(render.cpu().numpy(), o_render * o_mask) < 2e-5
+
+
+def test_nhwc_inpainting_path_equals_the_layered_one():
+    """Inpaint.pointcloud_inpainting on CUDA keeps everything NHWC between the context convolutions, the 68-channel splat and
+    the GridNet (_pointcloud_inpainting_b200); it must give what _render_inputs() + forward(tensorData=, tensorMasks=) give."""
+    from ken_burns_effect_b200.models.pointcloud_inpainting import Inpaint
+    torch.manual_seed(3)
+    W, H, focal = 256, 192, 128.0
+    img, disp = synthetic.synthetic_scene(W, H, seed=8)
+    ti = torch.from_numpy(img[:, :, ::-1].copy()).permute(2, 0, 1).float().div(255).view(1, 3, H, W).cuda()
+    td = torch.from_numpy(disp).view(1, 1, H, W).cuda()
+    net = kb_helpers.deterministic_state(Inpaint()).cuda().eval()
+    shift = torch.tensor([6.0, -4.0, -15.0], device="cuda").view(1, 3, 1)
+    oc = {'dblFocal': focal, 'dblBaseline': 120, 'intWidth': W, 'intHeight': H}
+    with torch.no_grad():
+        render, existing = net._render_inputs(ti, td, shift, oc, None)
+        want = net.forward(tensorData=render, tensorMasks=existing)
+        # the fused path, stage by stage
+        depth = (focal * 120) / (td + 0.0000001)
+        valid = (kb.spatial_filter(td / td.max(), 'laplacian').abs() < 0.03).float()
+        pts = kb.depth_to_points(depth * valid, focal).view(1, 3, -1) + shift
+        im, dn = net.normalize_images_disp(ti, td, not_normed=True)
+        buf, ex2 = net._render_rows_b200(im, dn, pts, oc, focal)
+        assert torch.equal(ex2, existing)
+        got_rows = buf[..., :68].permute(0, 3, 1, 2)
+        assert kb_helpers.rel_l2(got_rows.cpu().numpy(), render.cpu().numpy()) < 1e-5      # fp32 summation order only
+        assert torch.equal(buf[..., 68], existing[:, 0]) and float(buf[..., 69:].abs().max()) == 0.0
+        got = net.pointcloud_inpainting(ti, td, shift, oc)
+    assert torch.equal(got['tensorExisting'], want['tensorExisting'])
+    for k in ('tensorImage', 'tensorDisparity'):
+        # the two inputs differ by fp32 summation order (1e-5 above, as do two runs of the SAME path: the splat's atomics);
+        # 57 TF32 layers with random weights turn that into ~2e-3 at the output, so the bar is the one the networks have
+        # against the reference fixtures (tests/test_gpu_conv.py), not a tighter one
+        r = kb_helpers.rel_l2(got[k].cpu().numpy(), want[k].cpu().numpy())
+        assert r < 1e-2, f"{k}: rel L2 {r:.3e}"

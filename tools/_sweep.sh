@@ -1,3 +1,3 @@
-for b in 16 24 32; do python bench.py --steps 10 --warmup 3 --batch $b --no-cpu-baseline --no-full-pipeline | python -c "
+for nb in 0 64 32 16; do python tools/bench_conv.py --no-cudnn --only 13 --n_block $nb | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('batch', $b, round(d['value']), round(d['e2e']['value']), round(d['roofline']['frac'],3))"; done
+d=json.loads(sys.stdin.read()); print('n_block', $nb, d['case'], round(d['ms']*1000,1))"; done
