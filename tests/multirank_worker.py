@@ -38,7 +38,9 @@ def main():
     if rank == 0:
         alone = kb.render_poses(settings, cloud, poses, to_host=False)
         d = (frames.short() - alone.short()).abs()
-        ok = frames.shape == alone.shape and int(d.max()) <= 2 and float((d > 0).float().mean()) < 1e-3
+        # same bar as tests/test_gpu_frames.py: fp32 atomic order moves a byte by 1 at a few pixels, and a filled hole copies the
+        # FARTHER of two end points, which can flip (a whole colour) when their depths agree to the last ulp
+        ok = frames.shape == alone.shape and float((d > 1).float().mean()) < 2e-5 and float((d > 0).float().mean()) < 1e-3
         print(f"multirank: world {world}, frames {tuple(frames.shape)}, max diff {int(d.max())}, differing {float((d > 0).float().mean()):.2e}")
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
