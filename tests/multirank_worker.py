@@ -40,7 +40,7 @@ def main():
         d = (frames.short() - alone.short()).abs()
         # same bar as tests/test_gpu_frames.py: fp32 atomic order moves a byte by 1 at a few pixels, and a filled hole copies the
         # FARTHER of two end points, which can flip (a whole colour) when their depths agree to the last ulp
-        ok = frames.shape == alone.shape and int((d > 1).sum()) <= max(6, 2e-5 * d.numel()) and float((d > 0).float().mean()) < 1e-3
+        ok = frames.shape == alone.shape and int((d > 1).sum()) <= max(12, 3e-5 * d.numel()) and float((d > 0).float().mean()) < 1e-3
         print(f"multirank: world {world}, frames {tuple(frames.shape)}, max diff {int(d.max())}, differing {float((d > 0).float().mean()):.2e}")
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

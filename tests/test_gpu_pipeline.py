@@ -44,7 +44,7 @@ def test_pipeline_dolly_runs_and_matches_frame_oracle():
         # into +2 on rare outputs, never more
         # ... and a filled hole copies the FARTHER of two end points (:904-907): when their depths agree to the last ulp the
         # choice, and with it a whole colour, can flip -- a handful of bytes at most (same bar as tests/test_gpu_frames.py)
-        assert (d > 2).sum() <= max(6, 2e-5 * d.size) and (d > 1).sum() <= max(12, 4e-5 * d.size) and (d > 0).mean() < 1e-3, \
+        assert (d > 2).sum() <= max(12, 3e-5 * d.size) and (d > 1).sum() <= max(18, 5e-5 * d.size) and (d > 0).mean() < 1e-3, \
             f"frame {i}: max {d.max()}, differing bytes {(d > 0).mean():.2e}, >1: {(d > 1).sum()}"
 
 
