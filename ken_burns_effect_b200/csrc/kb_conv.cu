@@ -15,11 +15,16 @@
 //   * weights are pre-packed per (tap, 32-channel slice) as K-major [Cout][32] panels, TMA-loaded next to A.
 //   * both operands land in shared memory in the 128-byte swizzled K-major layout that tcgen05.mma reads
 //     through shared-memory descriptors; the accumulator (128 lanes x Npad fp32 columns) lives in TMEM.
-//   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2..5 = epilogue:
-//     tcgen05.ld the accumulator, + bias, + residual, then up to three outputs, each optionally passed
-//     through the next layer's PReLU, so that "PReLU -> conv" chains never need a separate elementwise pass.
-//   * a ring of `stages` shared-memory slots with full/empty mbarriers decouples TMA from the tensor pipe;
-//     small-N layers fit two CTAs per SM so one CTA's epilogue overlaps the other's main loop.
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (both run their loops as whole warps, one elected lane issues),
+//     warps 2..9 = epilogue: tcgen05.ld the accumulator, + bias, partial-conv renormalisation, + residual, then up to
+//     three outputs, each optionally passed through the next layer's PReLU and the consumer's mask, so that
+//     "PReLU -> conv" chains never need a separate elementwise pass.
+//   * a ring of `stages` shared-memory slots with full/empty mbarriers decouples TMA from the tensor pipe.
+// Two kernels: k_conv_tf32 (one TMA load per filter tap, any filter; two CTAs per SM so that one CTA's epilogue overlaps
+// the other's main loop) and the persistent k_conv_halo_tf32 (stride 1, k <= 3: one halo load per tile, taps are
+// descriptor offsets, resident filters, accumulator ring in TMEM) -- see the comment above it.
+// KB_CONV_DEBUG (bit mask, profiling experiments only -- results are WRONG with any bit set): 1 no epilogue stores,
+// 2 no MMAs, 4 no activation loads, 8 no TMEM reads; this is how DESIGN.md's "what bounds the kernel" numbers were taken.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -197,7 +202,7 @@ struct ConvKernelParams {
   int resident;         // all weight panels stay in shared memory for the life of the CTA
   int n_blocks;
   long work_items;      // tiles * n_blocks
-  int debug;            // KB_CONV_DEBUG (profiling experiments only): 1 = no epilogue stores, 2 = no MMAs
+  int debug;            // KB_CONV_DEBUG bit mask (profiling experiments only, see the file header)
 };
 
 
