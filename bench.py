@@ -242,7 +242,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=150)
-    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--batch", type=int, default=32, help="poses per launch with frames left on the device (host-bound frames: <= 16)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-pipeline", action="store_true")
@@ -392,7 +392,7 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"kbe {'--dolly ' if DOLLY else ''}{W}x{H} -> {args.frames}-frame 3D KBE (configs[{(2 if DOLLY else 1) if (W, H) == (1024, 768) else 3}]), per-frame render loop "
                                "(process_shift..resize, utils/common.py:222-260)",
-                   "frames_per_step_per_gpu": F, "points": N, "pixels": P, "poses_per_launch": renderer.batch,
+                   "frames_per_step_per_gpu": F, "points": N, "pixels": P, "poses_per_launch": renderer.batch, "poses_per_launch_e2e": min(renderer.batch, kb.FRAME_BATCH_TO_HOST),
                    "parallelism": f"frame-shard x{world}" + (" + NCCL broadcast of the cloud per step" if world > 1 else ""),
                    "cpu_affinity": (f"rank 0 bound to {len(numa)} cores near its GPU (NVML)" if numa else "unbound"),
                    "l2": "no explicit flush: each step streams ~0.8 GB of z-buffers/accumulators/frames (> 126 MB L2)"},

@@ -16,8 +16,11 @@ import torch
 
 from .. import _native as nat
 
-# frames rendered per fused launch group (kb_render_frames); bounded by KB_MAX_POSES
-FRAME_BATCH = 16
+# Poses rendered per fused launch group (kb_render_frames), bounded by KB_MAX_POSES.  Measured at 1024x768 (profiles/): 32 poses
+# per launch render 4.8 % faster than 16 when the frames stay on the device, but frames bound for host memory are copied
+# batch by batch on a second stream and overlap better in batches of 16 (end to end 19.7 k vs 18.6 k frames/s).
+FRAME_BATCH = 32
+FRAME_BATCH_TO_HOST = 16
 
 
 def _stream():
@@ -344,7 +347,7 @@ class FrameRenderer:
         to_host = not out_frames.is_cuda
         it = 0
         while done < n:
-            k = min(self.batch, n - done)
+            k = min(self.batch if not to_host else min(self.batch, FRAME_BATCH_TO_HOST), n - done)
             arr = (nat.KBPose * k)()
             for i in range(k):
                 sh, focal = poses[done + i]
