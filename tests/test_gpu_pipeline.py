@@ -4,6 +4,8 @@ pinned to the reference: the nn.Module mirrors on CPU fp32 (tests/test_models_cp
 every kernel (tests/test_oracle_golden.py).  Random-weight CNNs make chaotic disparities, so discrete
 decisions (laplacian validity, holes) can flip on 1e-6 differences between cuDNN and CPU convolutions: the
 bar here is statistical (mean abs byte difference), the exact bars live in the per-stage tests."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -127,3 +129,23 @@ def test_nhwc_inpainting_path_equals_the_layered_one():
         # against the reference fixtures (tests/test_gpu_conv.py), not a tighter one
         r = kb_helpers.rel_l2(got[k].cpu().numpy(), want[k].cpu().numpy())
         assert r < 1e-2, f"{k}: rel L2 {r:.3e}"
+
+
+def test_kbe_cli_end_to_end(tmp_path):
+    """kbe.py as a user runs it (random weights: no checkpoints offline): image file in, PNG frames + 3d_kbe.mp4 out."""
+    import subprocess
+    import sys
+    import cv2
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    img, _ = synthetic.synthetic_scene(386, 322, seed=9)          # not multiples of 4: kbe.py crops to 384x320 (kbe.py:109-114)
+    src = str(tmp_path / "in.png")
+    cv2.imwrite(src, img)
+    out = str(tmp_path / "out")
+    r = subprocess.run([sys.executable, os.path.join(root, "kbe.py"), "--in", src, "--out", out, "--random-weights", "--frames", "4",
+                        "--write-frames"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    frames = sorted(os.listdir(os.path.join(out, "frames")))
+    assert frames == ["0.png", "1.png", "2.png", "3.png"]
+    f0 = cv2.imread(os.path.join(out, "frames", "0.png"))
+    assert f0.shape == (320, 384, 3)
+    assert os.path.getsize(os.path.join(out, "3d_kbe.mp4")) > 1000
