@@ -382,7 +382,10 @@ def main():
         # per-launch dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the last `ncu --set full` capture of this
         # very command (tools/ncu_summary.py --traffic; K = 16 poses per launch like here)
         kernel_of = {"splat_min": "kf_splat_min", "degrid": "kf_degrid4", "splat_accum": "kf_accum", "resolve": "kf_resolve"}
-        traffic = json.load(open(tpath)).get(kernel_of[dom])
+        tj = json.load(open(tpath))
+        traffic = tj.get(kernel_of[dom])
+        if traffic is not None:      # captured at tj["_poses_per_launch"] poses per launch; this run averages avg_k
+            traffic = int(traffic * avg_k / tj.get("_poses_per_launch", 16))
     render_ms_per_call = sum(stages[k] for k in bytes_stage)
     whole = (40 * N + 72 * P) * avg_k / (render_ms_per_call * 1e-3) / 1e9
 
