@@ -18,6 +18,8 @@ same workload -- the reference itself has no CPU render path (its kernels are cu
 import argparse
 import json
 import os
+
+os.environ.setdefault("KB200_RANDOM_VGG", "1")   # synthetic weights: there are no checkpoints offline (explicit opt-in)
 import sys
 import threading
 import time

@@ -128,7 +128,8 @@ def main(argv):
     pipe = Pipeline(model_paths=paths, partial_inpainting=cfg['partial'], dolly=cfg['dolly'],
                     output_frames=cfg['output_frames'], pretrain=cfg['pretrained_refine'], d2=cfg['d2'], frames=cfg['frames'])
     with torch.no_grad():
-        return pipe((tensorImage + 1) / 2, zoom_settings, cfg['output_path'], pretrained_estim=cfg['pretrained_estim'])
+        return pipe((tensorImage + 1) / 2, zoom_settings, cfg['output_path'], inpaint_depth=cfg['inpaint_depth'],
+                    pretrained_estim=cfg['pretrained_estim'])
 
 
 if __name__ == '__main__':

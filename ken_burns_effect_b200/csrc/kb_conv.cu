@@ -1042,8 +1042,17 @@ static int make_act_map(EncodeTiledFn enc, const kb_conv_args *a, int box_w, int
   return 0;
 }
 
+// cudaFuncSetAttribute and the SM count are per DEVICE: one process may drive several GPUs, so the caches are keyed by it.
+static constexpr int kMaxDevices = 64;
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
 static int raise_smem_limit() {
-  static bool done = false;
+  static bool done_dev[kMaxDevices] = {};
+  bool &done = done_dev[current_device()];
   if (done) return 0;
   cudaError_t e = cudaFuncSetAttribute(k_conv_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
@@ -1057,10 +1066,10 @@ static int raise_smem_limit() {
 }
 
 static int sm_count() {
-  static int n = 0;
+  static int n_dev[kMaxDevices] = {};
+  const int dev = current_device();
+  int &n = n_dev[dev];
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   }
   return n;

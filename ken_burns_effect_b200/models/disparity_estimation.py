@@ -8,16 +8,39 @@ from ..utils import convstack as cs
 from .gridnet import Basic, add_grid, grid_forward, grid_name
 
 
+# Opt-in for a default-initialised VGG trunk (tests, benchmarks, `kbe.py --random-weights`, Pipeline(model_paths=None)):
+# set by those callers or by KB200_RANDOM_VGG=1.  Without it a missing ImageNet checkpoint is an error, never a silent
+# random network: Semantics' weights are in none of the released .tar files, so garbage here is garbage frames.
+ALLOW_RANDOM_VGG = False
+
+
 def _vgg19_bn_features():
-    """torchvision's VGG19-bn feature stack.  The reference asks for ImageNet weights
-    (disparity_estimation.py:86); they are loaded when the checkpoint file already sits in the local torch hub
-    cache and replaced by the default initialisation when it does not (no download is ever attempted: there is
-    no network in this environment).  The weights are not part of any released .tar checkpoint."""
+    """torchvision's VGG19-bn feature stack with the ImageNet weights the reference asks for
+    (disparity_estimation.py:86: vgg19_bn(pretrained=True)).  Order: an explicit state_dict file named by
+    KB200_VGG19_BN_WEIGHTS; torchvision's own loader (local hub cache, else download); and only with the explicit opt-in above a
+    default-initialised trunk, announced on stderr."""
     import os
+    import sys
+    explicit = os.environ.get('KB200_VGG19_BN_WEIGHTS')
+    if explicit:
+        vgg = torchvision.models.vgg19_bn(weights=None)
+        vgg.load_state_dict(torch.load(explicit, map_location='cpu'))
+        return vgg.features.eval()
     weights = torchvision.models.VGG19_BN_Weights.IMAGENET1K_V1
     cached = os.path.join(torch.hub.get_dir(), 'checkpoints', os.path.basename(weights.url))
-    if os.path.exists(cached):
-        return torchvision.models.vgg19_bn(weights=weights).features.eval()
+    random_ok = ALLOW_RANDOM_VGG or os.environ.get('KB200_RANDOM_VGG') == '1'
+    if os.path.exists(cached) or not random_ok:
+        try:
+            return torchvision.models.vgg19_bn(weights=weights).features.eval()
+        except Exception as exc:                                   # no network / unwritable cache
+            if not random_ok:
+                raise RuntimeError(
+                    "Semantics needs torchvision's ImageNet VGG19-bn weights (the reference loads vgg19_bn(pretrained=True)) and "
+                    f"they could not be loaded ({exc}).  Put {os.path.basename(weights.url)} into {os.path.dirname(cached)}, or "
+                    "point KB200_VGG19_BN_WEIGHTS at a state_dict file, or opt in to a randomly initialised trunk with "
+                    "--random-weights / KB200_RANDOM_VGG=1.") from exc
+    print("ken_burns_effect_b200: WARNING -- VGG19-bn trunk is RANDOMLY initialised (opt-in); disparities are meaningless",
+          file=sys.stderr)
     return torchvision.models.vgg19_bn(weights=None).features.eval()
 
 

@@ -279,12 +279,21 @@ def kenburns_poses(objectSettings, objectCommon):
 
 
 def process_inpaint(tensorShift, objectCommon, moduleInpaint, dblFocal):
-    """utils/common.py:47-81 (single-network branch; the list branch of the reference references an
-    undefined name and cannot run)."""
-    if isinstance(moduleInpaint, list):
-        moduleInpaint = moduleInpaint[0]
-    obj = moduleInpaint.pointcloud_inpainting(objectCommon['tensorRawImage'], objectCommon['tensorRawDisparity'],
-                                              tensorShift, objectCommon, dblFocal)
+    """utils/common.py:47-81.  A list [colour network, disparity network] (`kbe.py --inpaint-depth`) takes colour and the
+    existing-mask from the first and the disparity from the second, which is what the reference's list branch (:50-62) sets out
+    to do before it trips over an undefined name and a wrong key."""
+    if isinstance(moduleInpaint, (list, tuple)):
+        if len(moduleInpaint) != 2:
+            raise ValueError("process_inpaint: a list of inpainting networks must be [colour, disparity]")
+        col = moduleInpaint[0].pointcloud_inpainting(objectCommon['tensorRawImage'], objectCommon['tensorRawDisparity'],
+                                                     tensorShift, objectCommon, dblFocal)
+        dep = moduleInpaint[1].pointcloud_inpainting(objectCommon['tensorRawImage'], objectCommon['tensorRawDisparity'],
+                                                     tensorShift, objectCommon, dblFocal)
+        obj = dict(col)
+        obj['tensorDisparity'] = dep['tensorDisparity']
+    else:
+        obj = moduleInpaint.pointcloud_inpainting(objectCommon['tensorRawImage'], objectCommon['tensorRawDisparity'],
+                                                  tensorShift, objectCommon, dblFocal)
     disp = obj['tensorDisparity']
     depth = (dblFocal * objectCommon['dblBaseline']) / (disp + 0.0000001)
     valid = (spatial_filter(disp / disp.max(), 'laplacian').abs() < 0.03).float()
@@ -400,6 +409,8 @@ def crop_size(objectSettings):
 
 
 _PINNED = {}      # shape -> [pinned uint8 tensors]; cudaHostAlloc of 354 MB costs more than rendering 150 frames
+_PINNED_ORDER = []              # shapes, least recently used first
+PINNED_POOL_BYTES = 4 << 30     # idle buffers beyond this are released, oldest shape first
 _RENDERERS = {}   # (device, H, W, crop, baseline) -> FrameRenderer (workspace, staging buffers, copy stream)
 
 
@@ -407,13 +418,30 @@ def pinned_frames(shape):
     """A pinned uint8 host buffer of `shape`, recycled from earlier calls once nobody else holds it (numpy views made
     with .numpy() keep their tensor alive, so frames still in use by the caller are never overwritten)."""
     import sys
-    pool = _PINNED.setdefault(tuple(shape), [])
+    shape = tuple(int(v) for v in shape)
+    pool = _PINNED.setdefault(shape, [])
+    if shape in _PINNED_ORDER:
+        _PINNED_ORDER.remove(shape)
+    _PINNED_ORDER.append(shape)
     for t in pool:
         if sys.getrefcount(t) <= 3:          # the pool's list, the loop variable, getrefcount's argument
             return t
     t = torch.empty(*shape, dtype=torch.uint8).pin_memory()
     if len(pool) < 4:
         pool.append(t)
+    # bound the pool: varying image sizes / frame counts must not pile up pinned host memory
+    total = sum(b.numel() for bufs in _PINNED.values() for b in bufs)
+    for old in list(_PINNED_ORDER[:-1]):
+        if total <= PINNED_POOL_BYTES:
+            break
+        bufs = _PINNED.get(old, [])
+        idle = [b for b in bufs if sys.getrefcount(b) <= 3]
+        for b in idle:
+            bufs.remove(b)
+            total -= b.numel()
+        if not bufs:
+            _PINNED.pop(old, None)
+            _PINNED_ORDER.remove(old)
     return t
 
 

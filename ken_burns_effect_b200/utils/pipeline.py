@@ -33,6 +33,9 @@ class Pipeline():
         self.d2 = d2
         self.frames = frames
 
+        if model_paths is None:                  # freshly initialised everything: the VGG trunk too (explicit opt-in)
+            from ..models import disparity_estimation
+            disparity_estimation.ALLOW_RANDOM_VGG = True
         self.moduleSemantics = Semantics().to(device).eval()
         self.moduleDisparity = Disparity().to(device).eval()
         self.moduleRefine = (RefineP() if pretrain else Refine()).to(device).eval()
@@ -81,17 +84,22 @@ class Pipeline():
             'boolInpaint': True,
             'dolly': self.dolly,
         }
+        moduleInpaint = self.moduleInpaint
+        if inpaint_depth:                        # colour from the first network, disparity from the second (common.py:50-62)
+            if not hasattr(self, 'moduleInpaintDepth'):
+                raise ValueError("inpaint_depth=True needs a fourth checkpoint (model_paths[3]: the disparity inpainting network)")
+            moduleInpaint = [self.moduleInpaint, self.moduleInpaintDepth]
         rank, world = shard.world()
         if world == 1:
             self.estimate_depth(tensorImage)
-            numpyResult = process_kenburns(settings, self.objectCommon, self.moduleInpaint)
+            numpyResult = process_kenburns(settings, self.objectCommon, moduleInpaint)
         else:
             # one process per GPU (torchrun): rank 0 runs the CNN stage, the cloud is broadcast once, every rank
             # renders its interleaved share of the poses, rank 0 gathers and writes
             dev = torch.device('cuda', torch.cuda.current_device())
             if rank == 0:
                 self.estimate_depth(tensorImage)
-                prepare_cloud(settings, self.objectCommon, self.moduleInpaint)
+                prepare_cloud(settings, self.objectCommon, moduleInpaint)
             cloud = shard.broadcast_cloud(self.objectCommon if rank == 0 else None, dev, src=0)
             poses = kenburns_poses(settings, cloud)
             frames = shard.render_sharded(poses, lambda mine: render_poses(settings, cloud, mine, to_host=False))

@@ -147,6 +147,50 @@ def fill_disocclusion(inp, depth, want_xy=False):
     return (out, xy) if want_xy else out
 
 
+def fill_ends(inp, depth):
+    """fill_disocclusion that also reports, per hole pixel, the two end points of the winning ray -> (out, ends [B,H,W,4])."""
+    inp, pi = _f32(inp)
+    depth, pd = _f32(depth)
+    B, C, H, W = inp.shape
+    out = np.empty_like(inp)
+    ends = np.empty((B, H, W, 4), np.int32)
+    lib().kbo_fill_ends(pi, pd, B, C, H, W, out.ctypes.data_as(c_f32p), None, ends.ctypes.data_as(c_i32p))
+    return out, ends
+
+
+def frame_with_ties(xyz_shifted, rgbd, W, H, focal, baseline, crop_w, crop_h, rel_gap=1e-5):
+    """frame() assembled from the stage functions, plus a bool [H,W] map of the OUTPUT pixels whose bilinear footprint
+    (resize o getRectSubPix, common.py:256-257) touches a filled hole that was decided by a depth tie: a hole copies the
+    FARTHER of the two end points of its shortest ray (:904-907); when their rendered depths agree to `rel_gap` the winner
+    depends on the order of the fp32 atomicAdds of updateOutput (:641), in the reference as much as anywhere else."""
+    render, existing = render_pointcloud(np.asarray(xyz_shifted)[None], np.asarray(rgbd)[None], W, H, focal, baseline)
+    dmask = render[:, 3:4] * (existing > 0.0)
+    filled, ends = fill_ends(render, dmask)
+    u8 = to_uint8(filled[0])
+    out = resize_linear(getrectsubpix(u8, crop_w, crop_h, W / 2.0, H / 2.0), W, H)
+    e = ends[0]
+    hole = e[..., 0] >= 0
+    da = dmask[0, 0][np.clip(e[..., 1], 0, H - 1), np.clip(e[..., 0], 0, W - 1)]
+    db = dmask[0, 0][np.clip(e[..., 3], 0, H - 1), np.clip(e[..., 2], 0, W - 1)]
+    tie = hole & (np.abs(da - db) <= rel_gap * np.maximum(np.abs(da), np.abs(db)))
+    # a tie at end point level also decides every hole that copies the same pair; mark the holes themselves
+    # footprint of output pixel (X, Y): patch columns sx, sx+1 with sx = floor((X+.5)*cw/W-.5); render columns
+    # floor(ox+sx) .. floor(ox+sx+1)+1 with ox = W/2-(cw-1)/2  -> a 3x3 (at most) block; dilate generously by 2
+    ox, oy = W / 2.0 - (crop_w - 1) * 0.5, H / 2.0 - (crop_h - 1) * 0.5
+    X = np.arange(W)
+    Y = np.arange(H)
+    sx = np.floor((X + 0.5) * crop_w / W - 0.5)
+    sy = np.floor((Y + 0.5) * crop_h / H - 0.5)
+    rx0 = np.clip(np.floor(ox + sx).astype(np.int64) - 1, 0, W - 1)
+    ry0 = np.clip(np.floor(oy + sy).astype(np.int64) - 1, 0, H - 1)
+    t = tie.astype(np.int32)
+    ii = np.pad(t, ((1, 0), (1, 0))).cumsum(0).cumsum(1)                 # integral image
+    rx1 = np.clip(rx0 + 4, 0, W)
+    ry1 = np.clip(ry0 + 4, 0, H)
+    cnt = ii[ry1][:, rx1] - ii[ry0][:, rx1] - ii[ry1][:, rx0] + ii[ry0][:, rx0]
+    return out, cnt > 0, int(tie.sum())
+
+
 def to_uint8(render):
     """common.py:255 for one sample: render [>=3,H,W] float -> uint8 [H,W,3]."""
     render, pr = _f32(render)

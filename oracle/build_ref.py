@@ -36,6 +36,7 @@ SHAPES = [
     dict(H=768, W=1024, N=768 * 1024, C=4, focal=512.0, baseline=120, B=1),
     dict(H=768, W=1024, N=768 * 1024 + 70001, C=4, focal=512.0, baseline=120, B=1),
     dict(H=768, W=1024, N=768 * 1024, C=68, focal=512.0, baseline=120, B=1),
+    dict(H=2160, W=3840, N=2160 * 3840, C=4, focal=1920.0, baseline=120, B=1),      # configs[3]
 ]
 
 

@@ -309,8 +309,8 @@ KBO_API int kbo_render_pointcloud(const float *xyz, const float *data, int B, lo
 /* kernel_discfill_updateOutput (common.py:837-924).  input [B,C,H,W], depth [B,1,H,W] -> output (a clone
  * of input with hole pixels, depth <= 0, overwritten from the farther end of the shortest of 16 rays).
  * fill_xy (optional, [B,H,W,2] int32) receives the source pixel chosen for each hole (-1,-1 otherwise). */
-KBO_API void kbo_fill(const float *input, const float *depth, int B, int C, int H, int W, float *output,
-                      int32_t *fill_xy) {
+static void fill_impl(const float *input, const float *depth, int B, int C, int H, int W, float *output,
+                      int32_t *fill_xy, int32_t *ends) {
   static const float dx0[16] = {-1, 0, 1, 1, -1, 1, 2, 2, -2, -1, 1, 2, 3, 3, 3, 3};
   static const float dy0[16] = {1, 1, 1, 0, 2, 2, 1, -1, 3, 3, 3, 3, 2, 1, -1, -2};
   float dirx[16], diry[16];
@@ -327,9 +327,11 @@ KBO_API void kbo_fill(const float *input, const float *depth, int B, int C, int 
     const int y = (int)((i % P) / W), x = (int)(i % W);
     const float *dep = depth + b * P;
     if (fill_xy) fill_xy[2 * i] = fill_xy[2 * i + 1] = -1;
+    if (ends) ends[4 * i] = ends[4 * i + 1] = ends[4 * i + 2] = ends[4 * i + 3] = -1;
     if (dep[(long)y * W + x] > 0.0f) continue;
     float shortest = 1000000.0f;
     int fx = -1, fy = -1;
+    int e0 = -1, e1 = -1, e2 = -1, e3 = -1;
     for (int k = 0; k < 16; ++k) {
       float ax = (float)x, ay = (float)y, bx = (float)x, by = (float)y;
       int iax = 0, iay = 0, ibx = 0, iby = 0;
@@ -357,13 +359,28 @@ KBO_API void kbo_fill(const float *input, const float *depth, int B, int C, int 
         fx = iax; fy = iay;
         if (dep[(long)iay * W + iax] < dep[(long)iby * W + ibx]) { fx = ibx; fy = iby; }
         shortest = dist;
+        e0 = iax; e1 = iay; e2 = ibx; e3 = iby;
       }
     }
     if (fx == -1 || fy == -1) continue;
     if (fill_xy) { fill_xy[2 * i] = fx; fill_xy[2 * i + 1] = fy; }
+    if (ends) { ends[4 * i] = e0; ends[4 * i + 1] = e1; ends[4 * i + 2] = e2; ends[4 * i + 3] = e3; }
     for (int c = 0; c < C; ++c)
       output[(b * C + c) * P + (long)y * W + x] = input[(b * C + c) * P + (long)fy * W + fx];
   }
+}
+
+KBO_API void kbo_fill(const float *input, const float *depth, int B, int C, int H, int W, float *output,
+                      int32_t *fill_xy) {
+  fill_impl(input, depth, B, C, H, W, output, fill_xy, NULL);
+}
+
+/* Same, also reporting both end points (from-x, from-y, to-x, to-y; -1 for non-holes) of the winning ray of every hole: the
+ * only decision of the fill that depends on floating-point noise is which of the two is farther (:904-907), so a test can
+ * tell which hole pixels are decided by a depth tie. */
+KBO_API void kbo_fill_ends(const float *input, const float *depth, int B, int C, int H, int W, float *output,
+                           int32_t *fill_xy, int32_t *ends) {
+  fill_impl(input, depth, B, C, H, W, output, fill_xy, ends);
 }
 
 /* common.py:255 -- (render[0,0:3].transpose(1,2,0) * 255.0).clip(0,255).astype(uint8): fp32 multiply,

@@ -3,6 +3,7 @@ import sys
 
 import pytest
 
+os.environ.setdefault("KB200_RANDOM_VGG", "1")      # no network: tests run the VGG trunk with seeded weights (explicit opt-in)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for _p in (ROOT, os.path.join(ROOT, "tests")):
     if _p not in sys.path:

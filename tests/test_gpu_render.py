@@ -25,6 +25,7 @@ CASES = [
     (256, 192, 101.37, 0, 4),
     (1024, 768, 512.0, 0, 4),
     (1024, 768, 512.0, 70001, 4),
+    (3840, 2160, 1920.0, 0, 4),           # configs[3]
 ]
 
 

@@ -5,6 +5,8 @@ Prints one JSON line per case.  Usage (GPU box): python tools/bench_conv.py [--n
 import argparse
 import json
 import os
+
+os.environ.setdefault("KB200_RANDOM_VGG", "1")   # synthetic weights: there are no checkpoints offline (explicit opt-in)
 import sys
 
 import torch

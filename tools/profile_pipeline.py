@@ -2,6 +2,8 @@
 """Where the time of one full KBE goes on the GPU: torch.profiler (CUPTI) kernel table of Pipeline.estimate_depth +
 prepare_cloud + render_poses at 1024x768, random-init weights.  Usage (GPU box): python tools/profile_pipeline.py > out.md"""
 import os
+
+os.environ.setdefault("KB200_RANDOM_VGG", "1")   # synthetic weights: there are no checkpoints offline (explicit opt-in)
 import sys
 
 import numpy as np
