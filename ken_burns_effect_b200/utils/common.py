@@ -414,31 +414,45 @@ PINNED_POOL_BYTES = 4 << 30     # idle buffers beyond this are released, oldest 
 _RENDERERS = {}   # (device, H, W, crop, baseline) -> FrameRenderer (workspace, staging buffers, copy stream)
 
 
+def _storage_users(t):
+    """How many tensors / numpy arrays share t's storage.  `tensor.numpy()` hangs a NEW tensor wrapper on the array (its .base),
+    so the Python refcount of `t` itself says nothing about frames a caller still holds; the storage's use count does.
+    None when this torch build does not expose the counter: such a buffer is then never recycled."""
+    try:
+        return int(torch._C._storage_Use_Count(t.untyped_storage()._cdata))
+    except Exception:
+        return None
+
+
 def pinned_frames(shape):
-    """A pinned uint8 host buffer of `shape`, recycled from earlier calls once nobody else holds it (numpy views made
-    with .numpy() keep their tensor alive, so frames still in use by the caller are never overwritten)."""
-    import sys
+    """A pinned uint8 host buffer of `shape`, recycled from earlier calls once nobody else holds its storage (frames handed out
+    as numpy views keep the storage in use, so they are never overwritten)."""
     shape = tuple(int(v) for v in shape)
     pool = _PINNED.setdefault(shape, [])
     if shape in _PINNED_ORDER:
         _PINNED_ORDER.remove(shape)
     _PINNED_ORDER.append(shape)
-    for t in pool:
-        if sys.getrefcount(t) <= 3:          # the pool's list, the loop variable, getrefcount's argument
-            return t
+
+    def idle(entry):
+        users = _storage_users(entry[0])
+        return users is not None and users <= entry[1]
+
+    for entry in pool:
+        if idle(entry):
+            return entry[0]
     t = torch.empty(*shape, dtype=torch.uint8).pin_memory()
-    if len(pool) < 4:
-        pool.append(t)
+    base = _storage_users(t)
+    if base is not None and len(pool) < 4:
+        pool.append((t, base))
     # bound the pool: varying image sizes / frame counts must not pile up pinned host memory
-    total = sum(b.numel() for bufs in _PINNED.values() for b in bufs)
+    total = sum(e[0].numel() for bufs in _PINNED.values() for e in bufs)
     for old in list(_PINNED_ORDER[:-1]):
         if total <= PINNED_POOL_BYTES:
             break
         bufs = _PINNED.get(old, [])
-        idle = [b for b in bufs if sys.getrefcount(b) <= 3]
-        for b in idle:
-            bufs.remove(b)
-            total -= b.numel()
+        for e in [e for e in bufs if idle(e)]:
+            bufs.remove(e)
+            total -= e[0].numel()
         if not bufs:
             _PINNED.pop(old, None)
             _PINNED_ORDER.remove(old)

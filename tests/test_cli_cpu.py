@@ -52,3 +52,29 @@ def test_load_image_crops_to_multiple_of_4(tmp_path):
     ref = (torch.from_numpy(img[:36, :48]).permute(2, 0, 1).float() / 255 - 0.5) / 0.5
     assert torch.equal(t, ref)
     assert float(((t + 1) / 2).min()) >= 0.0
+
+
+def test_pinned_pool_never_recycles_frames_a_caller_still_holds(monkeypatch):
+    """process_kenburns returns numpy views of a pooled pinned buffer: while any of them is alive the buffer must not be handed
+    out again (tensor.numpy() hangs a new tensor wrapper on the array, so only the storage's use count tells)."""
+    import torch
+    from ken_burns_effect_b200.utils import common as kb
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)      # no CUDA here: plain host memory stands in
+    monkeypatch.setattr(kb, "_PINNED", {})
+    monkeypatch.setattr(kb, "_PINNED_ORDER", [])
+    a = kb.pinned_frames((2, 4, 4, 3))
+    ptr_a = a.data_ptr()
+    frames = a.numpy()
+    views = [frames[i] for i in range(2)]
+    del a, frames
+    b = kb.pinned_frames((2, 4, 4, 3))
+    assert b.data_ptr() != ptr_a
+    del views, b
+    c = kb.pinned_frames((2, 4, 4, 3))
+    assert c.data_ptr() == ptr_a
+    # byte cap: idle buffers of other shapes are released, oldest first
+    monkeypatch.setattr(kb, "PINNED_POOL_BYTES", 200)
+    del c
+    for n in range(3, 8):
+        kb.pinned_frames((n, 4, 4, 3))
+    assert sum(e[0].numel() for bufs in kb._PINNED.values() for e in bufs) <= 200 + 7 * 48
