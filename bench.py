@@ -39,6 +39,13 @@ METRIC = "novel-view frames/sec at 1024x768, 150-frame KBE"
 DOLLY = False
 
 
+def workload_name(frames):
+    """config.workload, identical in both arms (the driver compares the strings)."""
+    cfg = (2 if DOLLY else 1) if (W, H) == (1024, 768) else 3
+    return (f"kbe {'--dolly ' if DOLLY else ''}{W}x{H} -> {frames}-frame 3D KBE (configs[{cfg}]), per-frame render loop "
+            "(process_shift..resize, utils/common.py:222-260)")
+
+
 def build_workload(frames, world=1, rank=0):
     from ken_burns_effect_b200.utils import common as kb
     from ken_burns_effect_b200.utils import synthetic
@@ -120,6 +127,116 @@ def full_pipeline(steps=3, warmup=3, frames=150):
             "ms_cnn_and_inpaint_stage": 1e3 * t_cnn / steps, "ms_render_loop": 1e3 * t_render / steps, "points": int(npts),
             "conv_tflop_per_kbe": 2.30, "note": "random-init weights: the disparity is noise-like, so the appended point "
             "count and hole statistics are not those of a trained model; CNN forwards replay from CUDA graphs from their 4th call on (captured during warm-up)"}
+
+
+def _max_over_ranks(ms, world, dev):
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return ms
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def throughput_mode(rank, world, dev, images_per_gpu=8, frames=150):
+    """BASELINE configs[4]: a batch of images (64 at 8 GPUs), one full 150-frame KBE each, IMAGES sharded over the GPUs: every rank
+    runs the whole pipeline (depth CNNs, two inpainting passes, render loop, frames into pinned host memory) on its own images --
+    replicas, no collective on the data path, one barrier on each side of the timed region.  Images start in pinned host memory."""
+    import torch
+    import torch.distributed as dist
+    from ken_burns_effect_b200.utils import common as kb
+    from ken_burns_effect_b200.utils import synthetic
+    from ken_burns_effect_b200.utils.pipeline import Pipeline
+    torch.manual_seed(1234)
+    imgs = []
+    for i in range(images_per_gpu):
+        img, _ = synthetic.synthetic_scene(1024, 768, seed=1234 + rank * images_per_gpu + i)
+        imgs.append(torch.from_numpy(img).permute(2, 0, 1).contiguous().float().div(255).view(1, 3, 768, 1024).pin_memory())
+    pipe = Pipeline(model_paths=None, dolly=False, frames=frames)
+    zoom = synthetic.default_zoom(1024, 768)
+    settings = {'dblSteps': np.linspace(0.0, 1.0, frames).tolist(), 'objectFrom': zoom['objectFrom'],
+                'objectTo': zoom['objectTo'], 'boolInpaint': True, 'dolly': False}
+
+    def one(t):
+        pipe.estimate_depth(t)
+        kb.prepare_cloud(settings, pipe.objectCommon, pipe.moduleInpaint)
+        out = kb.render_poses(settings, pipe.objectCommon, kb.kenburns_poses(settings, pipe.objectCommon))   # synchronises
+        return out
+
+    for t in imgs[:4]:                      # warm-up: weight packing, CUDA-graph capture of the forwards, pinned pool
+        one(t)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for t in imgs:
+        one(t)
+    torch.cuda.synchronize()
+    ms = 1e3 * (time.perf_counter() - t0)
+    if world > 1:
+        dist.barrier()
+    ms = _max_over_ranks(ms, world, dev)
+    n_img = images_per_gpu * world
+    return {"what": f"configs[4]: {n_img} images of 1024x768, one {frames}-frame KBE each, {images_per_gpu} images per GPU, full pipeline "
+                    "per rank (image in pinned host memory -> frames in pinned host memory), TF32 tcgen05 convolutions",
+            "images_per_s": n_img / (ms / 1e3), "frames_per_s": n_img * frames / (ms / 1e3), "ms_per_image_per_gpu": ms / images_per_gpu,
+            "images": n_img, "dtype_cnn": "tf32", "weights": "random-init (no checkpoints offline)"}
+
+
+def config3_4k(rank, world, dev, frames=300, steps=3, warmup=2):
+    """BASELINE configs[3]: 3840x2160 input, 300-frame KBE, frames sharded over the GPUs after ONE broadcast of the cloud
+    (10.2 M points, 286 MB).  Render loop only, like the headline metric; device-resident and end to end."""
+    import torch
+    import torch.distributed as dist
+    from ken_burns_effect_b200.utils import common as kb
+    from ken_burns_effect_b200.utils import shard, synthetic
+    w4, h4, f4 = 3840, 2160, 1920.0
+    zoom = synthetic.default_zoom(w4, h4)
+    cloud0, packed_host, packed = None, None, None
+    if rank == 0:
+        pts, rgb, dep, common = synthetic.scene_cloud(w4, h4, seed=1234, focal=f4, baseline=BASELINE, inpaint_standin=True)
+        n = pts.shape[1]
+        packed_host = torch.from_numpy(np.concatenate([pts, rgb, dep], 0)).pin_memory()
+        packed = packed_host.to(dev)
+        cloud0 = dict(common)
+        cloud0.update(intWidth=w4, intHeight=h4, tensorInpaPoints=packed[0:3].view(1, 3, n), tensorInpaImage=packed[3:6].view(1, 3, n),
+                      tensorInpaDepth=packed[6:7].view(1, 1, n), tensorPacked=packed)
+    xchg = shard.CloudExchange(dev, 3 * w4 * h4 // 2, src=0)
+    cloud = xchg.broadcast(cloud0)
+    st = {'dblSteps': np.linspace(0.0, 1.0, frames).tolist(), 'objectFrom': zoom['objectFrom'], 'objectTo': zoom['objectTo'], 'dolly': False}
+    poses = kb.kenburns_poses(st, cloud)[rank::world]
+    cw, ch = kb.crop_size(st)
+    r = kb.FrameRenderer(cloud['tensorInpaPoints'], cloud['tensorInpaImage'], cloud['tensorInpaDepth'], w4, h4, BASELINE, cw, ch, batch=16)
+    fdev = torch.empty(len(poses), h4, w4, 3, dtype=torch.uint8, device=dev)
+    fhost = torch.empty(len(poses), h4, w4, 3, dtype=torch.uint8).pin_memory()
+
+    def run(dst, h2d):
+        for i in range(warmup + steps):
+            if i == warmup:
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            if h2d and rank == 0:
+                packed.copy_(packed_host, non_blocking=True)
+            c = xchg.broadcast(cloud0)
+            r.set_cloud(c['tensorInpaPoints'], c['tensorInpaImage'], c['tensorInpaDepth'])
+            r.render_into(poses, dst)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return _max_over_ranks(e0.elapsed_time(e1), world, dev)
+
+    ms_d = run(fdev, False)
+    ms_e = run(fhost, True)
+    return {"what": f"configs[3]: 3840x2160 -> {frames}-frame KBE, poses rank::{world} per GPU, one NCCL broadcast of the cloud per effect",
+            "points": int(cloud['tensorInpaPoints'].shape[-1]), "value": frames * steps / (ms_d / 1e3), "unit": "frames/s",
+            "ms_per_effect": ms_d / steps,
+            "e2e": {"value": frames * steps / (ms_e / 1e3), "unit": "frames/s", "ms_per_effect": ms_e / steps,
+                    "d2h_bytes_per_effect": int(frames * h4 * w4 * 3)}}
 
 
 def cpu_cnn_stage():
@@ -208,11 +325,12 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sample / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "kbe 1024x768 -> 150-frame 3D KBE (configs[1]), per-frame render loop",
+        "config": {"workload": workload_name(args.frames),
                    "note": "reference has no CPU render path (cupy-only kernels); this is the C/OpenMP restatement "
                            "of its kernels + its numpy/OpenCV tail (oracle/kb_oracle.c)"},
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "per_step_frames_per_s": [round(x, 2) for x in vals],
     })
 
 
@@ -249,6 +367,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-pipeline", action="store_true")
     ap.add_argument("--dolly", action="store_true", help="BASELINE configs[2]: the dolly-zoom path (per-pose focal length, no inpainted points)")
+    ap.add_argument("--images-per-gpu", type=int, default=8, help="throughput mode (configs[4]): images per GPU, one full KBE each")
+    ap.add_argument("--config3", action="store_true", help="also run configs[3] (3840x2160, 300 frames, sharded) at this N; default only at N=8")
     ap.add_argument("--size", default="1024x768", help="WxH of the synthetic input (BASELINE configs[3]: 3840x2160 --frames 300)")
     args = ap.parse_args()
     global W, H, FOCAL, METRIC, DOLLY
@@ -294,29 +414,32 @@ def main():
     def cloud_on_rank0():
         c = dict(common)
         c.update(tensorInpaPoints=packed[0:3].view(1, 3, N), tensorInpaImage=packed[3:6].view(1, 3, N),
-                 tensorInpaDepth=packed[6:7].view(1, 1, N))
+                 tensorInpaDepth=packed[6:7].view(1, 1, N), tensorPacked=packed)
         return c
 
     renderer = kb.FrameRenderer(packed[0:3], packed[3:6], packed[6:7], W, H, BASELINE, cw, ch, batch=args.batch)
     frames_dev = torch.empty(F, H, W, 3, dtype=torch.uint8, device=dev)
     frames_host = torch.empty(F, H, W, 3, dtype=torch.uint8).pin_memory()
 
+    xchg = shard.CloudExchange(dev, N, src=0) if world > 1 else None
+
     def exchange():
-        # the path's one exchange step (ken_burns_effect_b200/utils/shard.py): the cloud travels over NVLink once per effect
-        c = shard.broadcast_cloud(cloud_on_rank0() if rank == 0 else None, dev, src=0)
+        # the path's one exchange step (ken_burns_effect_b200/utils/shard.py): the cloud travels over NVLink once per effect;
+        # preallocated receive buffer, header on a host side channel -> no stream drain, no allocation, no re-pack
+        c = xchg.broadcast(cloud_on_rank0() if rank == 0 else None)
         renderer.set_cloud(c['tensorInpaPoints'], c['tensorInpaImage'], c['tensorInpaDepth'])
 
     def step_device():
         if world > 1:
             exchange()
-        renderer.render_into(poses, frames_dev)
+        renderer.render_into(poses, frames_dev[:len(poses)])
 
     def step_e2e():
         if rank == 0:
             packed.copy_(packed_host, non_blocking=True)
         if world > 1:
             exchange()
-        renderer.render_into(poses, frames_host)
+        renderer.render_into(poses, frames_host[:len(poses)])
 
     def timed(fn, steps, warmup, profile=False):
         for _ in range(warmup):
@@ -366,6 +489,20 @@ def main():
     value = total_frames / (ms / 1000.0)
     e2e_value = total_frames / (ms_e2e / 1000.0)
 
+    # 4) the metric's own configuration at N GPUs: ONE args.frames-pose effect split N ways (strong scaling) -- the same
+    #    exchange, every rank renders poses rank::world of the single path
+    strong = None
+    if world > 1:
+        all_poses = build_workload(args.frames, 1, 0)[4]
+        weak_poses = poses
+        poses = all_poses[rank::world]
+        ms_s, _, _ = timed(step_device, args.steps, args.warmup)
+        ms_se, _, _ = timed(step_e2e, args.steps, args.warmup)
+        poses = weak_poses
+        strong = {"what": f"one {args.frames}-pose effect split over {world} GPUs (poses rank::{world}), cloud broadcast per effect",
+                  "value": args.frames * args.steps / (ms_s / 1000.0), "unit": "frames/s", "ms_per_effect": ms_s / args.steps,
+                  "e2e": {"value": args.frames * args.steps / (ms_se / 1000.0), "unit": "frames/s", "ms_per_effect": ms_se / args.steps}}
+
     P = W * H
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -395,8 +532,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"kbe {'--dolly ' if DOLLY else ''}{W}x{H} -> {args.frames}-frame 3D KBE (configs[{(2 if DOLLY else 1) if (W, H) == (1024, 768) else 3}]), per-frame render loop "
-                               "(process_shift..resize, utils/common.py:222-260)",
+        "config": {"workload": workload_name(args.frames),
                    "frames_per_step_per_gpu": F, "points": N, "pixels": P, "poses_per_launch": renderer.batch, "poses_per_launch_e2e": min(renderer.batch, kb.FRAME_BATCH_TO_HOST),
                    "parallelism": f"frame-shard x{world}" + (" + NCCL broadcast of the cloud per step" if world > 1 else ""),
                    "cpu_affinity": (f"rank 0 bound to {len(numa)} cores near its GPU (NVML)" if numa else "unbound"),
@@ -414,9 +550,25 @@ def main():
                                                  "bytes_per_frame": 40 * N + 72 * P}},
         "stage_ms_per_launch": stages,
     }
+    if strong is not None:
+        out["strong_scaling"] = strong
+    del renderer, frames_dev, frames_host
+    torch.cuda.empty_cache()
+    if not args.no_full_pipeline:
+        try:
+            tm = throughput_mode(rank, world, dev, args.images_per_gpu, args.frames)
+        except Exception as e:
+            tm = {"error": f"{type(e).__name__}: {e}"}
+        if rank == 0:
+            out["throughput_mode"] = tm
+    if (world == 8 or args.config3) and (W, H) == (1024, 768) and not DOLLY:
+        try:
+            c3 = config3_4k(rank, world, dev)
+        except Exception as e:
+            c3 = {"error": f"{type(e).__name__}: {e}"}
+        if rank == 0:
+            out["config3_4k"] = c3
     if rank == 0 and world == 1 and not args.no_full_pipeline:
-        del renderer, frames_dev
-        torch.cuda.empty_cache()
         try:
             out["kbe_full_pipeline"] = full_pipeline()
         except Exception as e:   # the headline numbers above must survive a failure of this extra leg

@@ -212,6 +212,14 @@ int kb_maxpool2_ceil(const float *x, long x_stride, int N, int H, int W, int C, 
 int kb_nchw_to_nhwc(const float *x, int N, int C, int H, int W, float *y, long y_stride, float sub, float mul, kb_stream_t stream);
 int kb_nhwc_to_nchw(const float *x, long x_stride, int N, int C, int H, int W, float *y, float mul, float add, kb_stream_t stream);
 
+/* ---- process_autozoom, utils/common.py:114-170 -------------------------------------------------- */
+/* For K (<= KB_MAX_POSES) camera shifts of one cloud xyz [3,N] (unshifted): counts[k] = number of pixels where the `existing` map
+ * of render_pointcloud(process_shift(points, shift_k), ...) is > 0 (:154-160: the score the reference maximises over a 16 x 16
+ * grid of candidate windows with one full render each).  counts: device int[K]; workspace: kb_coverage_workspace_bytes. */
+size_t kb_coverage_workspace_bytes(int H, int W, int K);
+int kb_coverage(const float *xyz, long N, const kb_pose *poses_host, int K, int H, int W, double baseline, void *workspace,
+                int *counts, kb_stream_t stream);
+
 /* ---- self-test ------------------------------------------------------------------------------------ */
 /* The kernels replace the fp64 sub-expressions the reference's source substitution creates (utils/common.py:453,
  * :467-470, :556-561, :639) and the IEEE divisions of the frame tail (:686, :255) by cheaper fp32 sequences that are

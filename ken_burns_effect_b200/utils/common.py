@@ -278,6 +278,72 @@ def kenburns_poses(objectSettings, objectCommon):
     return poses
 
 
+def process_autozoom(objectSettings, objectCommon):
+    """utils/common.py:114-170: pick the end window of an automatic zoom -- among a 16 x 16 grid of centre shifts within
+    +-objectSettings['dblShift'], the one whose view of the RAW cloud covers the most pixels (existing > 0).  The reference's
+    version cannot run (its process_shift call, :146-152, lacks the objectCommon argument); this is that function with the call
+    completed.  The (up to) 256 candidate views are rendered through the multi-pose z-buffer kernels in groups of KB_MAX_POSES
+    (kb_coverage) instead of 256 x (clone + 3 kernels + 2 reductions + .item())."""
+    n = 16
+    shift_u = np.linspace(-objectSettings['dblShift'], objectSettings['dblShift'], n)[None, :].repeat(n, 0)
+    shift_v = np.linspace(-objectSettings['dblShift'], objectSettings['dblShift'], n)[:, None].repeat(n, 1)
+    frm = objectSettings['objectFrom']
+    crop_w = frm['intCropWidth'] / objectSettings['dblZoom']
+    crop_h = frm['intCropHeight'] / objectSettings['dblZoom']
+    depth_from = objectCommon['objectDepthrange'][0]
+    depth_to = objectCommon['objectDepthrange'][0] * (crop_w / frm['intCropWidth'])
+    cands = []
+    for iu in range(n):
+        for iv in range(n):
+            su, sv = shift_u[iu, iv].item(), shift_v[iu, iv].item()
+            if frm['dblCenterU'] + su < crop_w / 2.0 or frm['dblCenterU'] + su > objectCommon['intWidth'] - (crop_w / 2.0):
+                continue
+            if frm['dblCenterV'] + sv < crop_h / 2.0 or frm['dblCenterV'] + sv > objectCommon['intHeight'] - (crop_h / 2.0):
+                continue
+            sx, sy, sz = _shift_scalars({'dblShiftU': su, 'dblShiftV': sv, 'dblDepthFrom': depth_from, 'dblDepthTo': depth_to},
+                                        objectCommon, objectCommon['dblFocal'])
+            cands.append((su, sv, np.array([sx, sy, sz], dtype=np.float64).astype(np.float32)))
+    if not cands:
+        raise ValueError("process_autozoom: no candidate window fits the image")
+    cover = coverage_counts(objectCommon['tensorRawPoints'], [c[2] for c in cands], objectCommon['intWidth'], objectCommon['intHeight'],
+                            objectCommon['dblFocal'], objectCommon['dblBaseline'])
+    best, best_u, best_v = 0.0, None, None
+    for (su, sv, _), cnt in zip(cands, cover):            # the reference's scan order and strict '<' (:160-164)
+        if best < cnt:
+            best, best_u, best_v = cnt, su, sv
+    if best_u is None:
+        raise ValueError("process_autozoom: every candidate view is empty")
+    return {'dblCenterU': frm['dblCenterU'] + best_u, 'dblCenterV': frm['dblCenterV'] + best_v,
+            'intCropWidth': int(round(frm['intCropWidth'] / objectSettings['dblZoom'])),
+            'intCropHeight': int(round(frm['intCropHeight'] / objectSettings['dblZoom']))}
+
+
+def coverage_counts(tensorPoints, shifts, intWidth, intHeight, dblFocal, dblBaseline):
+    """For each camera shift (fp32 triple): how many pixels of render_pointcloud(process_shift(points), ...)'s `existing` map are
+    > 0 (utils/common.py:154-160) -> list of ints.  existing > 0 at a pixel iff some point's gated bilinear weight reaches it, which
+    does not depend on the data channels: the z-buffer passes and a weight-only accumulation decide it."""
+    _need_cuda(tensorPoints)
+    L = nat.lib()
+    xyz = tensorPoints.reshape(3, -1).contiguous()
+    N = xyz.shape[1]
+    H, W = int(intHeight), int(intWidth)
+    out = []
+    K = nat.KB_MAX_POSES
+    ws = torch.empty(L.kb_coverage_workspace_bytes(H, W, K) + 256, device=xyz.device, dtype=torch.uint8)
+    ws_ptr = ws.data_ptr() + ((-ws.data_ptr()) % 256)
+    counts = torch.empty(K, device=xyz.device, dtype=torch.int32)
+    for a in range(0, len(shifts), K):
+        grp = shifts[a:a + K]
+        arr = (nat.KBPose * len(grp))()
+        for i, sh in enumerate(grp):
+            arr[i].shift[0], arr[i].shift[1], arr[i].shift[2] = float(sh[0]), float(sh[1]), float(sh[2])
+            arr[i].focal = float(dblFocal)
+        nat.check(L.kb_coverage(_ptr(xyz), N, arr, len(grp), H, W, float(dblBaseline), ctypes.c_void_p(ws_ptr), _ptr(counts), _stream()),
+                  "kb_coverage")
+        out += counts[:len(grp)].tolist()
+    return out
+
+
 def process_inpaint(tensorShift, objectCommon, moduleInpaint, dblFocal):
     """utils/common.py:47-81.  A list [colour network, disparity network] (`kbe.py --inpaint-depth`) takes colour and the
     existing-mask from the first and the disparity from the second, which is what the reference's list branch (:50-62) sets out
@@ -346,9 +412,12 @@ class FrameRenderer:
         else:
             self.rgbd = torch.cat([img, dep], 0).contiguous()
 
-    def render_into(self, poses, out_frames):
+    def render_into(self, poses, out_frames, on_batch=None):
         """poses: list of (shift fp32[3], focal); out_frames: uint8 tensor [len(poses),H,W,3] (device or
-        pinned host).  Enqueue only -- the caller synchronises the current stream."""
+        pinned host).  Enqueue only -- the caller synchronises the current stream.
+        on_batch(start, count, event): called after every batch has been enqueued, `event` fires when out_frames[start:start+count]
+        is complete (after the device-to-host copy for host destinations) -- utils/sink.py consumes frames this way while the
+        next batch renders."""
         L = nat.lib()
         n = len(poses)
         done = 0
@@ -378,6 +447,14 @@ class FrameRenderer:
                 with torch.cuda.stream(self.copy_stream):
                     dst.copy_(target, non_blocking=True)
                     self.ev_copied[slot].record(self.copy_stream)
+                    if on_batch is not None:
+                        ev = torch.cuda.Event()
+                        ev.record(self.copy_stream)
+                        on_batch(done, k, ev)
+            elif on_batch is not None:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                on_batch(done, k, ev)
             done += k
             it += 1
         if to_host:
@@ -459,9 +536,10 @@ def pinned_frames(shape):
     return t
 
 
-def render_poses(objectSettings, objectCommon, poses, to_host=True):
+def render_poses(objectSettings, objectCommon, poses, to_host=True, sink=None, out=None):
     """Stage B, utils/common.py:222-260, for the given poses of the path -> uint8 [len(poses),H,W,3]
-    (pinned host memory when to_host, else on the cloud's device)."""
+    (pinned host memory when to_host, else on the cloud's device).  sink: a utils.sink.FrameSink that receives the frames batch
+    by batch while later batches still render (host destinations only); out: destination to use instead of a pooled buffer."""
     crop_w, crop_h = crop_size(objectSettings)
     pts = objectCommon['tensorInpaPoints']
     key = (pts.device, int(objectCommon['intHeight']), int(objectCommon['intWidth']), crop_w, crop_h, float(objectCommon['dblBaseline']))
@@ -473,20 +551,30 @@ def render_poses(objectSettings, objectCommon, poses, to_host=True):
                                                    objectCommon['dblBaseline'], crop_w, crop_h)
     else:
         renderer.set_cloud(pts, objectCommon['tensorInpaImage'], objectCommon['tensorInpaDepth'])
-    if to_host:
-        out = pinned_frames((len(poses), renderer.H, renderer.W, 3))
-    else:
-        out = torch.empty(len(poses), renderer.H, renderer.W, 3, dtype=torch.uint8, device=renderer.device)
+    if out is None:
+        if to_host:
+            out = pinned_frames((len(poses), renderer.H, renderer.W, 3))
+        else:
+            out = torch.empty(len(poses), renderer.H, renderer.W, 3, dtype=torch.uint8, device=renderer.device)
+    feeder = None
+    if sink is not None:
+        if out.is_cuda:
+            raise RuntimeError("render_poses: a frame sink consumes host frames (to_host=True)")
+        from .sink import BatchFeeder
+        feeder = BatchFeeder(sink, out)
     if len(poses):
-        renderer.render_into(poses, out)
+        renderer.render_into(poses, out, on_batch=feeder)
     torch.cuda.current_stream(renderer.device).synchronize()
+    if feeder is not None:
+        feeder.finish()
     return out
 
 
-def process_kenburns(objectSettings, objectCommon, moduleInpaint):
-    """utils/common.py:172-263 -> list of uint8 [H,W,3] frames (RGB order of the input tensor's channels)."""
+def process_kenburns(objectSettings, objectCommon, moduleInpaint, sink=None):
+    """utils/common.py:172-263 -> list of uint8 [H,W,3] frames (RGB order of the input tensor's channels).
+    sink (additive): a utils.sink.FrameSink fed while the frames render."""
     if 'boolInpaint' not in objectSettings or objectSettings['boolInpaint'] == True:  # noqa: E712
         prepare_cloud(objectSettings, objectCommon, moduleInpaint)
     poses = kenburns_poses(objectSettings, objectCommon)
-    frames = render_poses(objectSettings, objectCommon, poses).numpy()
+    frames = render_poses(objectSettings, objectCommon, poses, sink=sink).numpy()
     return [frames[i] for i in range(len(poses))]

@@ -4,7 +4,8 @@ Same constructor and __call__ signature.  Differences, all additive or dead-code
   * the Mask R-CNN the reference builds and never uses (pipeline.py:36) is not built;
   * `model_paths=None` keeps the freshly initialised weights (tests, benchmarks -- no checkpoints offline);
   * `frames` (default 75 like pipeline.py:104,113) selects the number of rendered poses;
-  * the mp4 is written with cv2.VideoWriter (moviepy is not installed here), same 25 fps ping-pong sequence;
+  * the mp4 is written with cv2.VideoWriter (moviepy is not installed here), same 25 fps ping-pong sequence, and PNGs / video
+    are encoded by an asynchronous sink (utils/sink.py) while the frames still render;
   * the per-frame loop runs fused on the device (utils.common.process_kenburns).
 """
 import os
@@ -19,7 +20,7 @@ from ..models.disparity_refinement_pretrained import Refine as RefineP
 from ..models.partial_inpainting import Inpaint as PartialInpaint
 from ..models.pointcloud_inpainting import Inpaint
 from . import shard
-from .common import depth_to_points, kenburns_poses, prepare_cloud, process_kenburns, render_poses
+from .common import depth_to_points, kenburns_poses, prepare_cloud, render_poses
 from .utils import device, load_models, resize_image
 
 
@@ -77,6 +78,12 @@ class Pipeline():
 
     @torch.no_grad()
     def __call__(self, tensorImage, zoom_settings, output_path=None, inpaint_depth=False, pretrained_estim=False):
+        """-> list of uint8 [H,W,3] frames (every rank gets the whole list under torchrun).  With output_path the frames go to an
+        asynchronous sink (utils/sink.py) while they render: <out>/frames/<i>.png when output_frames, <out>/3d_kbe.mp4 always --
+        the files of pipeline.py:120-134.  self.last_timing holds the wall-clock breakdown of the call."""
+        import time
+        from .sink import FrameSink
+        t_start = time.perf_counter()
         settings = {
             'dblSteps': np.linspace(0.0, 1.0, self.frames).tolist(),
             'objectFrom': zoom_settings['objectFrom'],
@@ -90,40 +97,78 @@ class Pipeline():
                 raise ValueError("inpaint_depth=True needs a fourth checkpoint (model_paths[3]: the disparity inpainting network)")
             moduleInpaint = [self.moduleInpaint, self.moduleInpaintDepth]
         rank, world = shard.world()
+        timing = {}
+        dev = torch.device(device)
+
+        def mark(name):
+            if dev.type == 'cuda':
+                torch.cuda.synchronize(dev)
+            timing[name] = time.perf_counter() - t_start
+
         if world == 1:
             self.estimate_depth(tensorImage)
-            numpyResult = process_kenburns(settings, self.objectCommon, moduleInpaint)
-        else:
-            # one process per GPU (torchrun): rank 0 runs the CNN stage, the cloud is broadcast once, every rank
-            # renders its interleaved share of the poses, rank 0 gathers and writes
-            dev = torch.device('cuda', torch.cuda.current_device())
-            if rank == 0:
-                self.estimate_depth(tensorImage)
-                prepare_cloud(settings, self.objectCommon, moduleInpaint)
-            cloud = shard.broadcast_cloud(self.objectCommon if rank == 0 else None, dev, src=0)
-            poses = kenburns_poses(settings, cloud)
-            frames = shard.render_sharded(poses, lambda mine: render_poses(settings, cloud, mine, to_host=False))
-            if rank != 0:
-                return None
-            frames = frames.cpu().numpy()
+            mark('t_depth_stage_s')
+            prepare_cloud(settings, self.objectCommon, moduleInpaint)
+            mark('t_inpaint_stage_s')
+            sink = None
+            if output_path is not None:
+                sink = FrameSink(output_path, self.frames, write_frames=self.output_frames, write_video=True,
+                                 rgb_to_bgr=pretrained_estim, t0=t_start)
+            poses = kenburns_poses(settings, self.objectCommon)
+            frames = render_poses(settings, self.objectCommon, poses, sink=sink).numpy()
+            mark('t_frames_in_host_memory_s')
             numpyResult = [frames[i] for i in range(len(poses))]
+            if sink is not None:
+                timing.update(sink.close())
+            timing['t_total_s'] = time.perf_counter() - t_start
+            self.last_timing = timing
+            return numpyResult
 
-        if self.output_frames and output_path is not None:
-            frames_dir = os.path.join(output_path, 'frames')
-            os.makedirs(frames_dir, exist_ok=True)
-            for idx, frame in enumerate(numpyResult):
-                if pretrained_estim:
-                    frame = cv2.cvtColor(frame, cv2.COLOR_RGB2BGR)
-                cv2.imwrite(os.path.join(frames_dir, str(idx) + '.png'), frame)
-
-        if output_path is not None:
-            os.makedirs(output_path, exist_ok=True)
-            seq = numpyResult + list(reversed(numpyResult))[1:]          # ping-pong, pipeline.py:132-134
-            h, w = seq[0].shape[:2]
-            vw = cv2.VideoWriter(os.path.join(output_path, '3d_kbe.mp4'), cv2.VideoWriter_fourcc(*'mp4v'), 25, (w, h))
-            for f in seq:
-                # moviepy expects RGB; the reference flips BGR tensors with [:, :, ::-1] unless pretrained_estim.
-                # cv2.VideoWriter expects BGR, i.e. the tensor's own channel order in the default case.
-                vw.write(np.ascontiguousarray(f if not pretrained_estim else f[:, :, ::-1]))
-            vw.release()
+        # One process per GPU (torchrun): rank 0 runs the CNN stage, the cloud is broadcast once, every rank renders its
+        # interleaved share of the poses and copies it over ITS OWN PCIe link into a shared host segment (shard.SharedFrames);
+        # PNGs are written by the rank that rendered them, the video by rank 0 from the shared segment.
+        if rank == 0:
+            self.estimate_depth(tensorImage)
+            prepare_cloud(settings, self.objectCommon, moduleInpaint)
+            mark('t_cnn_stages_s')
+        H, W = int(tensorImage.size(2)), int(tensorImage.size(3))
+        ex = getattr(self, '_exchange', None)
+        if ex is None or ex.buf.numel() < 7 * 3 * H * W:
+            ex = self._exchange = shard.CloudExchange(dev, 3 * H * W, src=0)       # each inpainting pass appends at most H*W points
+        cloud = ex.broadcast(self.objectCommon if rank == 0 else None)
+        poses = kenburns_poses(settings, cloud)
+        key = (len(poses), H, W)
+        if getattr(self, '_shared_key', None) != key:
+            if getattr(self, '_shared', None) is not None:
+                self._shared.close()
+            self._shared, self._shared_key = shard.SharedFrames(len(poses), H, W), key
+        shared = self._shared
+        mine = shard.shard_indices(len(poses), rank, world)
+        sink = None
+        if output_path is not None and self.output_frames:
+            sink = FrameSink(output_path, len(mine), write_frames=True, write_video=False, rgb_to_bgr=pretrained_estim,
+                             frame_indices=mine, t0=t_start)
+        render_poses(settings, cloud, [poses[i] for i in mine], sink=sink, out=shared.block())
+        mark('t_own_frames_in_host_memory_s')
+        torch.distributed.barrier()                      # every block of the shared segment is complete
+        numpyResult = [shared.frame(i) for i in range(len(poses))]
+        if sink is not None:
+            timing.update(sink.close())
+        if output_path is not None and rank == 0:
+            video = FrameSink(output_path, len(poses), write_frames=False, write_video=True, rgb_to_bgr=pretrained_estim, t0=t_start)
+            video.submit(0, _as_batch(numpyResult))
+            timing.update({'video_' + k: v for k, v in video.close().items()})
+        timing['t_total_s'] = time.perf_counter() - t_start
+        self.last_timing = timing
         return numpyResult
+
+
+class _as_batch:
+    """A list of equally shaped frames behind the [k,H,W,3] indexing FrameSink.submit uses (no copy)."""
+
+    def __init__(self, frames):
+        self.frames = frames
+        self.shape = (len(frames),) + tuple(frames[0].shape)
+
+    def __getitem__(self, i):
+        return self.frames[i]

@@ -53,13 +53,19 @@ def pack_cloud(objectCommon):
     N = pts.shape[-1]
     packed = torch.cat([pts.reshape(3, N), objectCommon['tensorInpaImage'].reshape(3, N),
                         objectCommon['tensorInpaDepth'].reshape(1, N)], 0).contiguous().float()
+    return packed, cloud_header(objectCommon)
+
+
+def cloud_header(objectCommon):
+    """The scalars of objectCommon the per-frame loop reads, as 16 doubles (host tensor)."""
+    N = objectCommon['tensorInpaPoints'].shape[-1]
     rng = objectCommon['objectDepthrange']
     hdr = torch.zeros(HEADER_DOUBLES, dtype=torch.float64)
     vals = [N, objectCommon['intHeight'], objectCommon['intWidth'], objectCommon['dblFocal'], objectCommon['dblBaseline'],
             rng[0], rng[1], rng[2][0], rng[2][1], rng[3][0], rng[3][1],
             objectCommon.get('dblDispmin', 0.0), objectCommon.get('dblDispmax', 0.0)]
     hdr[:len(vals)] = torch.tensor(vals, dtype=torch.float64)
-    return packed, hdr
+    return hdr
 
 
 def unpack_cloud(packed, hdr):
@@ -96,6 +102,108 @@ def broadcast_cloud(objectCommon, device, src=0, group=None):
         packed = torch.empty(7, int(hdr[0].item()), dtype=torch.float32, device=device)
     dist.broadcast(packed, src=src, group=group)       # 28 * N bytes over NVLink
     return unpack_cloud(packed, hdr.cpu())
+
+
+class CloudExchange:
+    """The exchange step without a stream drain: a preallocated receive buffer, the 128-byte header on a HOST side channel
+    (a gloo group: the non-source ranks learn N without reading anything back from their GPU, so the kernels of the previous
+    effect keep running while the host already posts the next broadcast), then ONE broadcast of exactly 28*N payload bytes
+    into the buffer.  On the source rank the cloud is sent from where it lies when it is already packed ([7,N] contiguous,
+    objectCommon['tensorPacked']), else three device copies place it in the buffer (no torch.cat, no fresh allocation).
+    """
+
+    def __init__(self, device, capacity_points, src=0, group=None):
+        self.device, self.src, self.group = device, src, group
+        self.buf = torch.empty(7 * int(capacity_points), dtype=torch.float32, device=device)
+        self.host_group = None
+        rank, R = world()
+        if R > 1:
+            backend = dist.get_backend(group)
+            self.host_group = group if backend == 'gloo' else dist.new_group(backend='gloo')
+
+    def _fit(self, n):
+        if 7 * n > self.buf.numel():                       # rare: a cloud larger than promised -- grow once, keep it
+            self.buf = torch.empty(7 * n, dtype=torch.float32, device=self.device)
+
+    def broadcast(self, objectCommon):
+        """objectCommon: read on the source rank only (None elsewhere) -> the unpacked cloud on every rank."""
+        rank, R = world()
+        if R == 1:
+            packed, hdr = pack_cloud(objectCommon)
+            return unpack_cloud(packed.to(self.device), hdr)
+        hdr = torch.zeros(HEADER_DOUBLES, dtype=torch.float64)
+        send = None
+        if rank == self.src:
+            hdr = cloud_header(objectCommon)
+            n = int(hdr[0])
+            pk = objectCommon.get('tensorPacked')
+            if pk is not None and pk.is_contiguous() and tuple(pk.shape) == (7, n) and pk.device == self.buf.device:
+                send = pk.view(-1)
+            else:
+                self._fit(n)
+                send = self.buf[:7 * n]
+                v = send.view(7, n)
+                v[0:3].copy_(objectCommon['tensorInpaPoints'].reshape(3, n))
+                v[3:6].copy_(objectCommon['tensorInpaImage'].reshape(3, n))
+                v[6:7].copy_(objectCommon['tensorInpaDepth'].reshape(1, n))
+        dist.broadcast(hdr, src=self.src, group=self.host_group)            # host to host: no GPU involved
+        n = int(hdr[0])
+        if rank != self.src:
+            self._fit(n)
+            send = self.buf[:7 * n]
+        dist.broadcast(send, src=self.src, group=self.group)                # 28 * N bytes over NVLink, stream-ordered
+        return unpack_cloud(send.view(7, n), hdr)
+
+
+class SharedFrames:
+    """Host frames of one effect in a POSIX shared-memory segment that every rank of the box maps and page-locks: rank r
+    copies ITS frames device-to-host over ITS OWN PCIe link straight into its block, and the rank that writes the video reads
+    all blocks from host memory -- no gather through one GPU, no second host copy.  Block r holds the frames of the poses
+    r, r+R, r+2R, ... in order (shard_indices)."""
+
+    def __init__(self, n_total, H, W, tag="kb200"):
+        import os
+        rank, R = world()
+        self.rank, self.R, self.n_total, self.H, self.W = rank, R, int(n_total), int(H), int(W)
+        self.counts = [len(range(r, self.n_total, R)) for r in range(R)]
+        self.offsets = [sum(self.counts[:r]) for r in range(R)]
+        self.frame_bytes = self.H * self.W * 3
+        nbytes = max(1, self.n_total * self.frame_bytes)
+        port = os.environ.get("MASTER_PORT", "0")
+        self.path = f"/dev/shm/{tag}_{port}_{self.n_total}x{self.H}x{self.W}"
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(nbytes)
+        if R > 1:
+            dist.barrier()
+        self.flat = torch.from_file(self.path, shared=True, size=nbytes, dtype=torch.uint8)
+        self.pinned = False
+        if torch.cuda.is_available():
+            rc = torch.cuda.cudart().cudaHostRegister(self.flat.data_ptr(), nbytes, 0)
+            self.pinned = int(rc) == 0
+        if R > 1:
+            dist.barrier()
+        if rank == 0:
+            try:
+                os.unlink(self.path)              # the mappings keep the memory alive; nothing is left behind in /dev/shm
+            except OSError:
+                pass
+
+    def block(self, r=None):
+        """uint8 [n_r,H,W,3] view of rank r's block (default: this rank's)."""
+        r = self.rank if r is None else r
+        a = self.offsets[r] * self.frame_bytes
+        return self.flat[a:a + self.counts[r] * self.frame_bytes].view(self.counts[r], self.H, self.W, 3)
+
+    def frame(self, i):
+        """uint8 [H,W,3] numpy view of pose i, wherever it was rendered."""
+        r, j = i % self.R, i // self.R
+        return self.block(r)[j].numpy()
+
+    def close(self):
+        if self.pinned:
+            torch.cuda.cudart().cudaHostUnregister(self.flat.data_ptr())
+            self.pinned = False
 
 
 def gather_frames(local_frames, n_total, dst=0, group=None):

@@ -3,6 +3,7 @@
 {nb_iter, model_state_dict, optimizer_<type>_state_dict, scheduler_<type>_state_dict}."""
 import os
 
+import cv2
 import torch
 import torch.nn.functional as F
 
@@ -51,3 +52,57 @@ def load_models(models_list, models_paths, continue_training=False):
             entry['model'].load_state_dict(ckpt)
             print('Pre-trained model ' + entry['type'] + ' loaded succesfully.')
     return iter_nb
+
+
+# ---------------------------------------------------------------------------------------------------------
+# batched (B > 1) callers of the render operators -- utils/utils.py:221-300, :370-377 of the reference (training-time view
+# synthesis: the only callers of generate_mask and of render_pointcloud with B > 1)
+# ---------------------------------------------------------------------------------------------------------
+
+def get_item_in_dict(dict_in, idx):
+    """utils/utils.py:370-377: sample `idx` of a (nested) dict of batched values."""
+    return {k: (get_item_in_dict(v, idx) if isinstance(v, dict) else v[idx]) for k, v in dict_in.items()}
+
+
+def get_tensor_shift(objectCommon):
+    """utils/utils.py:221-245: the camera shift of the END pose (dblStep = 1) of objectCommon['zoomSettings'] -> [1,3,1].
+    Same scalars as the reference's process_shift call; the clone of the whole cloud it makes and drops is not made."""
+    from . import common as kb
+    zoom = objectCommon['zoomSettings']
+    st, focal = kb._pose_settings({'objectFrom': zoom['objectFrom'], 'objectTo': zoom['objectTo'], 'dolly': False}, objectCommon, 1.0)
+    sx, sy, sz = kb._shift_scalars(st, objectCommon, objectCommon['dblFocal'])
+    return torch.FloatTensor([sx, sy, sz]).view(1, 3, 1).to(objectCommon['tensorRawPoints'].device)
+
+
+def get_masks(tensorImage, tensorDisparity, tensorDepth, zoom_settings, camera, AFromB=True, tensorContext=None):
+    """utils/utils.py:248-300: per-sample camera shifts from batched zoom settings, then either the disocclusion masks of the
+    shifted views (AFromB: generate_mask, B >= 1 in one launch group) or the shifted renders themselves (render_pointcloud with
+    B >= 1, C = 4 or 68).  Same return tuples as the reference."""
+    from . import common as kb
+    B = tensorImage.shape[0]
+    dblFocal, dblBaseline = camera['focal'], camera['baseline']
+    intWidth, intHeight = tensorImage.shape[3], tensorImage.shape[2]
+    tensorValid = (kb.spatial_filter(tensorDisparity / tensorDisparity.max(), 'laplacian').abs() < 0.03).float()
+    tensorPoints = kb.depth_to_points(tensorDepth * tensorValid, dblFocal)
+    shiftList, objectList = [], []
+    depth_host = tensorDepth[:, 0, 128:-128, 128:-128].detach().cpu().numpy()      # one D2H for the whole batch
+    dmin = tensorDisparity.reshape(B, -1).min(1)[0].tolist()
+    dmax = tensorDisparity.reshape(B, -1).max(1)[0].tolist()
+    for idx in range(B):
+        oc = {'dblFocal': dblFocal, 'dblBaseline': dblBaseline, 'intWidth': intWidth, 'intHeight': intHeight,
+              'tensorRawImage': tensorImage[idx], 'tensorRawDisparity': tensorDisparity[idx],
+              'dblDispmin': dmin[idx], 'dblDispmax': dmax[idx],
+              'objectDepthrange': cv2.minMaxLoc(src=depth_host[idx], mask=None),
+              'tensorRawPoints': tensorPoints[idx].view(1, 3, -1),
+              'zoomSettings': get_item_in_dict(zoom_settings, idx)}
+        shiftList.append(get_tensor_shift(oc))
+        objectList.append(oc)
+    tensorShift = torch.cat(shiftList)
+    pts = tensorPoints.view(B, 3, -1)
+    if AFromB:
+        return kb.generate_mask(pts, tensorShift, intWidth, intHeight, dblFocal, dblBaseline), tensorShift, objectList
+    chans = [tensorImage, tensorDisparity] + ([tensorContext] if tensorContext is not None else [])
+    data = torch.cat(chans, 1)
+    tensorRender, tensorMasks = kb.render_pointcloud(pts + tensorShift, data.view(B, data.shape[1], -1), intWidth, intHeight,
+                                                     dblFocal, dblBaseline)
+    return tensorRender, (tensorMasks > 0.0).float(), pts, tensorShift, objectList

@@ -78,3 +78,30 @@ def test_pinned_pool_never_recycles_frames_a_caller_still_holds(monkeypatch):
     for n in range(3, 8):
         kb.pinned_frames((n, 4, 4, 3))
     assert sum(e[0].numel() for bufs in kb._PINNED.values() for e in bufs) <= 200 + 7 * 48
+
+
+def test_frame_sink_writes_pngs_and_pingpong_video(tmp_path):
+    """utils/sink.py against the files utils/pipeline.py:120-134 of the reference produces: <out>/frames/<i>.png (lossless) and
+    a 25 fps clip of forward + backward-without-the-turning-frame (2n-1 frames), fed in batches like the renderer does."""
+    import cv2
+    import numpy as np
+    from ken_burns_effect_b200.utils.sink import FrameSink
+    rng = np.random.default_rng(3)
+    frames = rng.integers(0, 255, (7, 48, 64, 3), dtype=np.uint8)
+    sink = FrameSink(str(tmp_path / "o"), 7, write_frames=True, write_video=True, frame_indices=[10, 11, 12, 13, 14, 15, 16])
+    sink.submit(0, frames[0:3])
+    sink.submit(3, frames[3:7])
+    st = sink.close()
+    assert st['frames'] == 7 and st['t_all_written_s'] >= st['t_first_frame_ready_s']
+    for j, i in enumerate(range(10, 17)):
+        assert (cv2.imread(str(tmp_path / "o" / "frames" / f"{i}.png")) == frames[j]).all()
+    cap = cv2.VideoCapture(str(tmp_path / "o" / "3d_kbe.mp4"))
+    assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == 13 and abs(cap.get(cv2.CAP_PROP_FPS) - 25) < 1e-6
+    # the colour flip of `pretrained_estim` (pipeline.py:125): PNGs hold the frame converted RGB -> BGR
+    sink = FrameSink(str(tmp_path / "p"), 2, write_frames=True, write_video=False, rgb_to_bgr=True)
+    sink.submit(0, frames[0:2])
+    sink.close()
+    assert (cv2.imread(str(tmp_path / "p" / "frames" / "1.png")) == frames[1][:, :, ::-1]).all()
+    import pytest
+    with pytest.raises(RuntimeError):
+        FrameSink(str(tmp_path / "q"), 3, write_video=False).close()       # frames missing

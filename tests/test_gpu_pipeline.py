@@ -51,18 +51,54 @@ def test_pipeline_dolly_runs_and_matches_frame_oracle():
 
 
 @pytest.mark.parametrize("partial", [False, True])
-def test_pipeline_with_inpainting_grows_the_cloud(partial):
-    """Full KBE with the two inpainting passes (dense Inpaint, and PartialInpaint = kbe.py --partial-conv)."""
+def test_pipeline_with_inpainting_bookkeeping_and_frames(partial):
+    """Full KBE with the two inpainting passes (dense Inpaint, and PartialInpaint = kbe.py --partial-conv; the dense one is pinned
+    end to end against the reference run in tests/test_gpu_reference_e2e.py).  Here: stage A appends exactly the pixels each pass
+    found missing, in raster order, with depth = f*B/(disparity+1e-7) of the network's disparity; and the frames are the oracle's
+    frames of the cloud the pipeline built (tie-aware bar of tests/test_gpu_frames.py)."""
     torch.manual_seed(1)
     W, H = 384, 320
     img, _ = synthetic.synthetic_scene(W, H, seed=6)
-    t = torch.from_numpy(img).permute(2, 0, 1).float().div(255).view(1, 3, H, W)
+    t = torch.from_numpy(img).permute(2, 0, 1).contiguous().float().div(255).view(1, 3, H, W)
     pipe = Pipeline(model_paths=None, partial_inpainting=partial, dolly=False, frames=3)
-    frames = pipe(t, synthetic.default_zoom(W, H))
+    calls = []
+    orig = pipe.moduleInpaint.pointcloud_inpainting
+
+    def spy(*a, **k):
+        out = orig(*a, **k)
+        calls.append({key: v.clone() for key, v in out.items()})
+        return out
+    pipe.moduleInpaint.pointcloud_inpainting = spy
+    zoom = synthetic.default_zoom(W, H)
+    frames = pipe(t, zoom)
     oc = pipe.objectCommon
     n = oc['tensorInpaPoints'].shape[-1]
-    assert n >= W * H and oc['tensorInpaImage'].shape[-1] == n and oc['tensorInpaDepth'].shape[-1] == n
-    assert len(frames) == 3 and frames[0].dtype == np.uint8 and np.isfinite(np.stack(frames)).all()
+    assert len(calls) == 2 and len(frames) == 3 and frames[0].dtype == np.uint8
+    start = W * H
+    for c in calls:
+        existing = c.get('tensorExistingInput', c['tensorExisting'])[:, 0:1]
+        idx = (existing.view(-1) == 0).nonzero()[:, 0]
+        stop = start + idx.numel()
+        assert torch.equal(oc['tensorInpaImage'][0, :, start:stop], c['tensorImage'].view(3, -1)[:, idx])
+        assert torch.equal(oc['tensorInpaDisparity'][0, :, start:stop], c['tensorDisparity'].view(1, -1)[:, idx])
+        depth = (oc['dblFocal'] * oc['dblBaseline']) / (c['tensorDisparity'] + 0.0000001)
+        assert torch.equal(oc['tensorInpaDepth'][0, :, start:stop], depth.view(1, -1)[:, idx])
+        start = stop
+    assert start == n and n > W * H
+    # frames == oracle frames of that cloud
+    st = {'dblSteps': np.linspace(0, 1, 3).tolist(), 'objectFrom': zoom['objectFrom'], 'objectTo': zoom['objectTo'], 'dolly': False}
+    poses = kb.kenburns_poses(st, oc)
+    cw, ch = kb.crop_size(st)
+    pts = oc['tensorInpaPoints'][0].cpu().numpy()
+    data = np.concatenate([oc['tensorInpaImage'][0].cpu().numpy(), oc['tensorInpaDepth'][0].cpu().numpy()], 0)
+    oracle.set_threads(0)
+    for i, (sh, f) in enumerate(poses):
+        ref, ties, _ = oracle.frame_with_ties(oracle.shift_points(pts, sh), data, W, H, f, oc['dblBaseline'], cw, ch)
+        d = np.abs(frames[i].astype(np.int16) - ref.astype(np.int16))
+        outside = d * (~ties)[..., None]
+        # random-weight networks hallucinate noise: thousands of points fight over every pixel, so order-dependent last-bit
+        # differences are far more frequent than on a real scene -- still at most 2 outside depth-tie footprints
+        assert int(outside.max()) <= 2 and (d > 0).mean() < 5e-3, f"frame {i}: max {outside.max()} outside ties, {(d > 0).mean():.2e} differ"
 
 
 def test_pointcloud_inpainting_render_inputs_vs_oracle():

@@ -337,3 +337,91 @@ def test_partial_inpaint_pointcloud_inpainting_vs_reference_1024(ref):
         rep[key + '_rel_l2'] = kb_helpers.rel_l2(mine[key].cpu().numpy(), theirs[key].cpu().numpy())
     REPORT['partial_inpaint_vs_reference_1024'] = rep
     assert rep['tensorImage_rel_l2'] < 5e-3 and rep['tensorDisparity_rel_l2'] < 5e-3, rep
+
+
+def _batch_inputs(W, H, focal, seeds):
+    imgs, disps = [], []
+    for sd in seeds:
+        img, disp = synthetic.synthetic_scene(W, H, sd)
+        imgs.append(torch.from_numpy(img).permute(2, 0, 1).contiguous().float().div(255))
+        disps.append(torch.from_numpy(disp).view(1, H, W))
+    image, disparity = torch.stack(imgs).cuda(), torch.stack(disps).cuda()
+    return image, disparity, (focal * 120) / (disparity + 1e-7)
+
+
+def test_get_masks_and_tensor_shift_vs_reference(ref):
+    """the batched (B = 2) training-time callers of the render operators, utils/utils.py:221-300 -- get_tensor_shift,
+    get_masks(AFromB=False) = render_pointcloud with B > 1, get_masks(AFromB=True) = generate_mask -- against the reference's own."""
+    from ken_burns_effect_b200.utils import utils as kutils
+    W, H, focal = 512, 384, 256.0
+    image, disparity, depth = _batch_inputs(W, H, focal, (21, 22))
+    z = synthetic.default_zoom(W, H)
+    zoom = {k: {kk: [vv, vv * (0.97 if 'Center' in kk else 1)] for kk, vv in z[k].items()} for k in ('objectFrom', 'objectTo')}
+    for k in zoom:
+        for kk in ('intCropWidth', 'intCropHeight'):
+            zoom[k][kk] = [int(v) for v in zoom[k][kk]]
+    camera = {'focal': focal, 'baseline': 120}
+    r_render, r_masks, r_pts, r_shift, r_objs = ref.utils.get_masks(image, disparity, depth, zoom, camera, AFromB=False)
+    m_render, m_masks, m_pts, m_shift, m_objs = kutils.get_masks(image, disparity, depth, zoom, camera, AFromB=False)
+    assert torch.equal(r_shift, m_shift) and torch.equal(r_pts, m_pts)
+    assert [o['objectDepthrange'] for o in r_objs] == [o['objectDepthrange'] for o in m_objs]
+    flips = int((r_masks != m_masks).sum())
+    assert flips <= max(16, int(0.004 * W * H)) * 2, f"existing masks differ at {flips} pixels"     # the reference's degrid race
+    keep = ~torch.nn.functional.max_pool2d((r_masks != m_masks).float(), 5, 1, 2).bool()
+    rep = {'mask_flips': flips, 'render_rel_l2': kb_helpers.rel_l2((m_render * keep).cpu().numpy(), (r_render * keep).cpu().numpy())}
+    assert rep['render_rel_l2'] < 1e-3, rep
+    r_m, r_s, _ = ref.utils.get_masks(image, disparity, depth, zoom, camera, AFromB=True)
+    m_m, m_s, _ = kutils.get_masks(image, disparity, depth, zoom, camera, AFromB=True)
+    assert torch.equal(r_s, m_s) and r_m.shape == m_m.shape == (2, 1, H, W)
+    rep['generate_mask_disagreement'] = float((r_m != m_m).float().mean())
+    REPORT['get_masks_vs_reference_512_B2'] = rep
+    assert rep['generate_mask_disagreement'] < 5e-3, rep        # the reference's kernel races (utils/common.py:755-765)
+
+
+def test_autozoom_vs_the_reference_loop(ref):
+    """process_autozoom (utils/common.py:114-170).  The reference's function cannot run (its process_shift call lacks
+    an argument); the ground truth is its own loop body executed with the reference's process_shift / render_pointcloud and that
+    argument supplied: per candidate window, the number of pixels with existing > 0."""
+    W, H, focal = 512, 384, 256.0
+    oc = _common(W, H, seed=31, focal=focal)
+    oc['tensorRawPoints'] = ref.common.depth_to_points(oc['tensorRawDepth'], focal).view(1, 3, -1)
+    frm = {'dblCenterU': W / 2.0, 'dblCenterV': H / 2.0, 'intCropWidth': W, 'intCropHeight': H}
+    settings = {'dblShift': 40.0, 'dblZoom': 1.25, 'objectFrom': frm}
+    # the reference's loop (:115-164), with objectCommon passed to process_shift
+    su = np.linspace(-settings['dblShift'], settings['dblShift'], 16)[None, :].repeat(16, 0)
+    sv = np.linspace(-settings['dblShift'], settings['dblShift'], 16)[:, None].repeat(16, 1)
+    cw, ch = frm['intCropWidth'] / settings['dblZoom'], frm['intCropHeight'] / settings['dblZoom']
+    d_from = oc['objectDepthrange'][0]
+    d_to = oc['objectDepthrange'][0] * (cw / frm['intCropWidth'])
+    ref_counts = {}
+    for iu in range(16):
+        for iv in range(16):
+            u, v = su[iu, iv].item(), sv[iu, iv].item()
+            if frm['dblCenterU'] + u < cw / 2.0 or frm['dblCenterU'] + u > W - (cw / 2.0):
+                continue
+            if frm['dblCenterV'] + v < ch / 2.0 or frm['dblCenterV'] + v > H - (ch / 2.0):
+                continue
+            pts = ref.common.process_shift({'tensorPoints': oc['tensorRawPoints'], 'dblShiftU': u, 'dblShiftV': v,
+                                            'dblDepthFrom': d_from, 'dblDepthTo': d_to}, oc)[0]
+            _, existing = ref.common.render_pointcloud(pts, oc['tensorRawImage'].view(1, 3, -1), W, H, focal, 120)
+            ref_counts[(u, v)] = (existing > 0.0).float().sum().item()
+    assert len(ref_counts) > 100
+    got = kb.process_autozoom(settings, oc)
+    assert got['intCropWidth'] == int(round(W / 1.25)) and got['intCropHeight'] == int(round(H / 1.25))
+    chosen = (got['dblCenterU'] - frm['dblCenterU'], got['dblCenterV'] - frm['dblCenterV'])
+    key = min(ref_counts, key=lambda k_: abs(k_[0] - chosen[0]) + abs(k_[1] - chosen[1]))
+    best = max(ref_counts.values())
+    # the reference's in-place degrid can move a count by a few pixels between two of its own runs
+    REPORT['autozoom_512'] = {'candidates': len(ref_counts), 'reference_best': best, 'reference_count_of_chosen': ref_counts[key]}
+    assert abs(key[0] - chosen[0]) < 1e-9 and abs(key[1] - chosen[1]) < 1e-9
+    assert ref_counts[key] >= best - 8, REPORT['autozoom_512']
+    # and the per-candidate counts themselves
+    shifts, order = [], []
+    for (u, v) in ref_counts:
+        sx, sy, sz = kb._shift_scalars({'dblShiftU': u, 'dblShiftV': v, 'dblDepthFrom': d_from, 'dblDepthTo': d_to}, oc, focal)
+        shifts.append(np.array([sx, sy, sz], dtype=np.float64).astype(np.float32))
+        order.append((u, v))
+    mine = kb.coverage_counts(oc['tensorRawPoints'], shifts, W, H, focal, 120)
+    worst = max(abs(m - ref_counts[k_]) for m, k_ in zip(mine, order))
+    REPORT['autozoom_512']['max_count_difference'] = worst
+    assert worst <= 8, worst

@@ -59,6 +59,30 @@ def _worker(rank, world_size, port, n_poses, q):
             ok &= frames is None
         idx, local = shard.render_sharded(poses, _fake_render(12, 16), gather=False)
         ok &= idx == list(range(rank, n_poses, world_size)) and local.shape[0] == len(idx)
+        # the sync-free exchange: preallocated buffer, header on the host side channel, two effects with different N in a row
+        ex = shard.CloudExchange(torch.device("cpu"), capacity_points=1200, src=0)
+        for n_pts in (1000, 700, 1500):                       # the last one outgrows the buffer
+            c = ex.broadcast(_fake_common(N=n_pts) if rank == 0 else None)
+            r2 = _fake_common(N=n_pts)
+            ok &= all(torch.equal(c[k], r2[k]) for k in ('tensorInpaPoints', 'tensorInpaImage', 'tensorInpaDepth'))
+            ok &= c['objectDepthrange'] == r2['objectDepthrange'] and c['tensorPacked'].shape == (7, n_pts)
+        # a cloud that is already packed is sent from where it lies
+        if rank == 0:
+            packed, hdr = shard.pack_cloud(_fake_common(N=900))
+            src_cloud = shard.unpack_cloud(packed, hdr)
+        c = ex.broadcast(src_cloud if rank == 0 else None)
+        ok &= torch.equal(c['tensorInpaImage'], _fake_common(N=900)['tensorInpaImage'])
+        # frames in a shared host segment: every rank fills its block, every rank sees all frames in pose order
+        sh = shard.SharedFrames(n_poses, 12, 16, tag=f"kb200test{port}")
+        mine = shard.shard_indices(n_poses, rank, world_size)
+        blk = sh.block()
+        ok &= blk.shape == (len(mine), 12, 16, 3)
+        for j, i in enumerate(mine):
+            blk[j] = (i * 7) % 251
+        dist.barrier()
+        ok &= all(bool((sh.frame(i) == (i * 7) % 251).all()) for i in range(n_poses))
+        dist.barrier()
+        sh.close()
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
