@@ -166,21 +166,30 @@ def throughput_mode(rank, world, dev, images_per_gpu=8, frames=150):
 
     for t in imgs[:4]:                      # warm-up: weight packing, CUDA-graph capture of the forwards, pinned pool
         one(t)
+    pipe.run_many(imgs[:2], zoom, keep=False)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    for t in imgs:
+    for t in imgs:                          # (a) one image after the other, the way kbe.py would be called in a loop
         one(t)
+    torch.cuda.synchronize()
+    ms_serial = 1e3 * (time.perf_counter() - t0)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    pipe.run_many(imgs, zoom, keep=False)   # (b) Pipeline.run_many: CNN stage of image i+1 overlaps the frame loop of image i
     torch.cuda.synchronize()
     ms = 1e3 * (time.perf_counter() - t0)
     if world > 1:
         dist.barrier()
     ms = _max_over_ranks(ms, world, dev)
+    ms_serial = _max_over_ranks(ms_serial, world, dev)
     n_img = images_per_gpu * world
     return {"what": f"configs[4]: {n_img} images of 1024x768, one {frames}-frame KBE each, {images_per_gpu} images per GPU, full pipeline "
                     "per rank (image in pinned host memory -> frames in pinned host memory), TF32 tcgen05 convolutions",
             "images_per_s": n_img / (ms / 1e3), "frames_per_s": n_img * frames / (ms / 1e3), "ms_per_image_per_gpu": ms / images_per_gpu,
+            "one_image_at_a_time": {"images_per_s": n_img / (ms_serial / 1e3), "ms_per_image_per_gpu": ms_serial / images_per_gpu},
             "images": n_img, "dtype_cnn": "tf32", "weights": "random-init (no checkpoints offline)"}
 
 
@@ -308,6 +317,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # Same process environment as the cpu_baseline leg of the GPU arm: the reference is a PyTorch program, and the OpenMP runtime
+    # PyTorch brings along is the one its CPU kernels (and this restatement, a plain `#pragma omp parallel for` per kernel) run on
+    # -- measured on the B200 box: 56 frames/s with it, 37 frames/s with the system libgomp loaded first (profiles/).
+    import torch  # noqa: F401
     # keep the whole run within a few minutes: ~60 s of CPU work spread over the timed steps
     budget = float(os.environ.get("KB_BENCH_CPU_BUDGET_S", "60"))       # seconds of CPU work over the timed steps
     per_step = max(1.0, budget / max(1, args.steps))

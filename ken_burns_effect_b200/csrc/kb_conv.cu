@@ -216,7 +216,8 @@ struct ConvKernelParams {
 // warps spent the tile waiting on those (L2-latency) loads and the kernel ran epilogue-bound at 14-35 % tensor-pipe
 // activity.  They now live in shared memory (staged once per CTA, zero-padded so every read is an unconditional float4),
 // the residual of a chunk is requested BEFORE the accumulator is waited for, and the TMEM load overlaps both.
-__device__ __forceinline__ float prelu1(float v, float s) { return fmaxf(v, 0.f) + s * fminf(v, 0.f); }
+// PReLU as torch computes it (x >= 0 ? x : w * x): a compare and a predicated multiply.
+__device__ __forceinline__ float prelu1(float v, float s) { return v < 0.f ? __fmul_rn(v, s) : v; }
 
 struct EpiSmem {
   const float *bias;              // [cpad]   (zeros when the layer has no bias); the slopes of output o follow at

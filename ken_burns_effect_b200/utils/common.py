@@ -504,6 +504,7 @@ def _storage_users(t):
 def pinned_frames(shape):
     """A pinned uint8 host buffer of `shape`, recycled from earlier calls once nobody else holds its storage (frames handed out
     as numpy views keep the storage in use, so they are never overwritten)."""
+    import sys
     shape = tuple(int(v) for v in shape)
     pool = _PINNED.setdefault(shape, [])
     if shape in _PINNED_ORDER:
@@ -511,8 +512,11 @@ def pinned_frames(shape):
     _PINNED_ORDER.append(shape)
 
     def idle(entry):
-        users = _storage_users(entry[0])
-        return users is not None and users <= entry[1]
+        # nobody holds the tensor object itself (refs here: the pool's tuple, `t`, getrefcount's argument) and nobody holds
+        # another view of its storage (numpy arrays made by .numpy(), slices)
+        t = entry[0]
+        users = _storage_users(t)
+        return sys.getrefcount(t) <= 3 and users is not None and users <= entry[1]
 
     for entry in pool:
         if idle(entry):

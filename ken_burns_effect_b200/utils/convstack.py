@@ -334,7 +334,7 @@ def graphed(owner, tag, fn, *tensors):
         static_in = [t.clone() for t in tensors]
         torch.cuda.current_stream().synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):    # a render thread may be launching on its own stream
             out = fn(*static_in)
         ent.update(graph=g, static_in=static_in, static_out=out)
     else:

@@ -163,6 +163,66 @@ class Pipeline():
         return numpyResult
 
 
+    @torch.no_grad()
+    def run_many(self, images, zoom_settings, consume=None, keep=True):
+        """Throughput mode (BASELINE configs[4]: many images, one effect each, per GPU): the same stages as __call__, software-
+        pipelined over the images on two CUDA streams -- the CNN stage of image i+1 (tensor-core bound: depth networks + two
+        inpainting passes) runs on one stream while a helper thread renders the frames of image i on another (HBM / PCIe bound:
+        the fused frame loop and the device-to-host copies into pinned memory).  The reference processes one image at a time
+        (utils/pipeline.py:63 asserts B == 1); each image here is still its own B == 1 pass, bit-for-bit the single-image result.
+
+        images: iterable of [1,3,H,W] tensors in [0,1] (host, ideally pinned); zoom_settings: one dict or one per image;
+        consume(i, frames): called from the render thread with the uint8 [n,H,W,3] pinned tensor of image i;
+        -> list of those tensors (None entries when keep is False)."""
+        import queue
+        import threading
+        dev = torch.device(device)
+        images = list(images)
+        zooms = zoom_settings if isinstance(zoom_settings, (list, tuple)) else [zoom_settings] * len(images)
+        results = [None] * len(images)
+        q = queue.Queue(maxsize=2)                      # at most two clouds wait for the renderer
+        err = []
+
+        def render_loop():
+            try:
+                torch.cuda.set_device(dev)
+                with torch.cuda.stream(torch.cuda.Stream(dev)):
+                    while True:
+                        item = q.get()
+                        if item is None:
+                            return
+                        i, oc, settings, ready = item
+                        torch.cuda.current_stream().wait_event(ready)
+                        out = render_poses(settings, oc, kenburns_poses(settings, oc))      # synchronises its own stream only
+                        if consume is not None:
+                            consume(i, out)
+                        if keep:
+                            results[i] = out
+            except Exception as e:                       # surfaced by the caller
+                err.append(e)
+                while q.get() is not None:
+                    pass
+
+        th = threading.Thread(target=render_loop, daemon=True)
+        th.start()
+        with torch.cuda.stream(torch.cuda.Stream(dev)):
+            for i, img in enumerate(images):
+                settings = {'dblSteps': np.linspace(0.0, 1.0, self.frames).tolist(), 'objectFrom': zooms[i]['objectFrom'],
+                            'objectTo': zooms[i]['objectTo'], 'boolInpaint': True, 'dolly': self.dolly}
+                self.estimate_depth(img)
+                prepare_cloud(settings, self.objectCommon, self.moduleInpaint)
+                ready = torch.cuda.Event()
+                ready.record()
+                q.put((i, dict(self.objectCommon), settings, ready))
+                if err:
+                    break
+        q.put(None)
+        th.join()
+        if err:
+            raise err[0]
+        return results
+
+
 class _as_batch:
     """A list of equally shaped frames behind the [k,H,W,3] indexing FrameSink.submit uses (no copy)."""
 

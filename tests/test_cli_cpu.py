@@ -69,9 +69,13 @@ def test_pinned_pool_never_recycles_frames_a_caller_still_holds(monkeypatch):
     del a, frames
     b = kb.pinned_frames((2, 4, 4, 3))
     assert b.data_ptr() != ptr_a
-    del views, b
+    del views
+    held = b                                   # a caller that keeps the tensor itself (Pipeline.run_many's result list)
+    ptr_b = b.data_ptr()
+    del b
     c = kb.pinned_frames((2, 4, 4, 3))
-    assert c.data_ptr() == ptr_a
+    assert c.data_ptr() == ptr_a and c.data_ptr() != ptr_b
+    del held
     # byte cap: idle buffers of other shapes are released, oldest first
     monkeypatch.setattr(kb, "PINNED_POOL_BYTES", 200)
     del c

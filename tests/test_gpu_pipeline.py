@@ -185,3 +185,28 @@ def test_kbe_cli_end_to_end(tmp_path):
     f0 = cv2.imread(os.path.join(out, "frames", "0.png"))
     assert f0.shape == (320, 384, 3)
     assert os.path.getsize(os.path.join(out, "3d_kbe.mp4")) > 1000
+
+
+def test_run_many_equals_one_image_at_a_time():
+    """Pipeline.run_many (throughput mode: CNN stage of image i+1 on one stream while a helper thread renders image i on another)
+    must return, per image, what Pipeline.__call__ returns for that image alone -- up to the summation-order noise two runs of
+    the same call show (splat atomics feeding random-weight networks)."""
+    torch.manual_seed(4)
+    W, H = 384, 320
+    pipe = Pipeline(model_paths=None, dolly=False, frames=4)
+    zoom = synthetic.default_zoom(W, H)
+    imgs = []
+    for sd in (11, 12, 13, 14, 15):
+        img, _ = synthetic.synthetic_scene(W, H, seed=sd)
+        imgs.append(torch.from_numpy(img).permute(2, 0, 1).contiguous().float().div(255).view(1, 3, H, W).pin_memory())
+    alone = [np.stack(pipe(t, zoom)) for t in imgs]
+    again = np.stack(pipe(imgs[0], zoom))
+    seen = []
+    many = pipe.run_many(imgs, zoom, consume=lambda i, fr: seen.append(i))
+    assert seen == [0, 1, 2, 3, 4] and len(many) == 5
+    noise = np.abs(again.astype(np.int16) - alone[0].astype(np.int16))
+    for i in range(5):
+        d = np.abs(many[i].numpy().astype(np.int16) - alone[i].astype(np.int16))
+        assert d.shape == (4, H, W, 3)
+        assert (d > 1).mean() <= max(1e-3, 3 * (noise > 1).mean()) and (d > 0).mean() <= max(5e-3, 3 * (noise > 0).mean()), \
+            f"image {i}: {(d > 0).mean():.2e} of bytes differ ({(d > 1).mean():.2e} by more than 1); run-to-run noise {(noise > 0).mean():.2e}"
