@@ -212,6 +212,12 @@ int kb_maxpool2_ceil(const float *x, long x_stride, int N, int H, int W, int C, 
 int kb_nchw_to_nhwc(const float *x, int N, int C, int H, int W, float *y, long y_stride, float sub, float mul, kb_stream_t stream);
 int kb_nhwc_to_nchw(const float *x, long x_stride, int N, int C, int H, int W, float *y, float mul, float add, kb_stream_t stream);
 
+/* ---- image front end, kbe.py:96-114 and :181 ----------------------------------------------------- */
+/* src: uint8 [H,W,3] as cv2.imread returns it (device memory); dst: float [3, H - H%4, W - W%4] = ((ToTensor -> Normalize(.5,.5))
+ * cropped to multiples of 4, + 1) / 2 -- the tensor kbe.py hands to Pipeline.__call__, bit for bit.  swap_rb: the
+ * cv2.cvtColor(BGR2RGB) of `--pretrained-estim` (kbe.py:97-98). */
+int kb_image_front_end(const unsigned char *src, int H, int W, int swap_rb, float *dst, kb_stream_t stream);
+
 /* ---- process_autozoom, utils/common.py:114-170 -------------------------------------------------- */
 /* For K (<= KB_MAX_POSES) camera shifts of one cloud xyz [3,N] (unshifted): counts[k] = number of pixels where the `existing` map
  * of render_pointcloud(process_shift(points, shift_k), ...) is > 0 (:154-160: the score the reference maximises over a 16 x 16

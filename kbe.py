@@ -116,10 +116,20 @@ def main(argv):
     cfg = parse(argv)
     init_distributed()
     print('Number of threads used: ', torch.get_num_threads())
-    tensorImage = load_image(cfg['input_path'], cfg['pretrained_estim'])
-    imgHeight, imgWidth = tensorImage.size(1), tensorImage.size(2)
+    if torch.cuda.is_available():
+        # decode on the host (cv2), everything after it on the device: 3 bytes per pixel cross PCIe and the result is the
+        # tensor load_image() + (x + 1) / 2 builds, bit for bit (tests/test_gpu_pipeline.py)
+        from ken_burns_effect_b200.utils.utils import image_to_tensor
+        img = cv2.imread(filename=cfg['input_path'], flags=cv2.IMREAD_COLOR)
+        if img is None:
+            raise FileNotFoundError(cfg['input_path'])
+        image01 = image_to_tensor(img, cfg['pretrained_estim'])
+        imgHeight, imgWidth = image01.size(2), image01.size(3)
+    else:
+        tensorImage = load_image(cfg['input_path'], cfg['pretrained_estim'])
+        imgHeight, imgWidth = tensorImage.size(1), tensorImage.size(2)
+        image01 = (tensorImage.view(1, 3, imgHeight, imgWidth) + 1) / 2
     zoom_settings = crop_windows(cfg, imgWidth, imgHeight)
-    tensorImage = tensorImage.view(1, 3, imgHeight, imgWidth)
     paths = None
     if not cfg['random_weights']:
         paths = [cfg['estim_path'], cfg['refine_path'], cfg['inpaint_path']]
@@ -128,7 +138,7 @@ def main(argv):
     pipe = Pipeline(model_paths=paths, partial_inpainting=cfg['partial'], dolly=cfg['dolly'],
                     output_frames=cfg['output_frames'], pretrain=cfg['pretrained_refine'], d2=cfg['d2'], frames=cfg['frames'])
     with torch.no_grad():
-        return pipe((tensorImage + 1) / 2, zoom_settings, cfg['output_path'], inpaint_depth=cfg['inpaint_depth'],
+        return pipe(image01, zoom_settings, cfg['output_path'], inpaint_depth=cfg['inpaint_depth'],
                     pretrained_estim=cfg['pretrained_estim'])
 
 

@@ -66,6 +66,7 @@ SIGNATURES = {
     "kb_frames_workspace_bytes": (c_size_t, [ctypes.POINTER(KBFrameParams), c_int]),
     "kb_render_frames": (c_int, [c_void, c_void, c_long, ctypes.POINTER(KBPose), c_int,
                                  ctypes.POINTER(KBFrameParams), c_void, c_void, c_void]),
+    "kb_image_front_end": (c_int, [c_void, c_int, c_int, c_int, c_void, c_void]),
     "kb_coverage_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "kb_coverage": (c_int, [c_void, c_long, ctypes.POINTER(KBPose), c_int, c_int, c_int, c_double, c_void, c_void, c_void]),
     "kb_conv_packed_floats": (c_long, [c_int, c_int, c_int]),

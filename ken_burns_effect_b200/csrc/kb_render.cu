@@ -698,3 +698,34 @@ int kb_selftest_arith(int which, const float *a, const float *b, long n, int W, 
 }
 
 }  // extern "C"
+
+// ---- image front end: kbe.py:96-114, :181 of the reference ------------------------------------------------------------
+// cv2.imread's uint8 HWC image -> transforms.ToTensor() (x / 255) -> transforms.Normalize(.5, .5) ((x - 0.5) / 0.5) -> crop of
+// height and width to multiples of 4 -> (x + 1) / 2, as ONE pass on the device: the host sends 3 bytes per pixel instead of
+// building three float images and sending 12.  Every operation is the IEEE fp32 operation torch's CPU kernels perform, in the
+// same order, so the tensor is bit-identical to the reference's.
+namespace kb {
+__global__ void __launch_bounds__(256) k_image_front_end(const unsigned char *__restrict__ src, int H, int W, int Hc, int Wc,
+                                                         int swap_rb, float *__restrict__ dst) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long Pc = (long)Hc * Wc;
+  if (i >= Pc) return;
+  const int y = (int)(i / Wc), x = (int)(i - (long)y * Wc);
+  const unsigned char *px = src + ((long)y * W + x) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float u = (float)px[swap_rb ? 2 - c : c];
+    const float t = __fdiv_rn(u, 255.0f);                                   // ToTensor
+    const float n = __fdiv_rn(__fsub_rn(t, 0.5f), 0.5f);                    // Normalize(mean .5, std .5)
+    dst[c * Pc + i] = __fdiv_rn(__fadd_rn(n, 1.0f), 2.0f);                  // (tensorImage + 1) / 2, kbe.py:181
+  }
+}
+}  // namespace kb
+
+extern "C" int kb_image_front_end(const unsigned char *src, int H, int W, int swap_rb, float *dst, kb_stream_t stream) {
+  KB_REQUIRE(src && dst && H >= 4 && W >= 4, "kb_image_front_end: bad arguments");
+  const int Hc = H - H % 4, Wc = W - W % 4;
+  kb::k_image_front_end<<<kb::cdiv((long)Hc * Wc, 256), 256, 0, (cudaStream_t)stream>>>(src, H, W, Hc, Wc, swap_rb, dst);
+  kb::count_launch();
+  return kb::check_launch("kb_image_front_end");
+}

@@ -164,7 +164,7 @@ class Pipeline():
 
 
     @torch.no_grad()
-    def run_many(self, images, zoom_settings, consume=None, keep=True):
+    def run_many(self, images, zoom_settings, consume=None, keep=True, trace=None):
         """Throughput mode (BASELINE configs[4]: many images, one effect each, per GPU): the same stages as __call__, software-
         pipelined over the images on two CUDA streams -- the CNN stage of image i+1 (tensor-core bound: depth networks + two
         inpainting passes) runs on one stream while a helper thread renders the frames of image i on another (HBM / PCIe bound:
@@ -173,10 +173,17 @@ class Pipeline():
 
         images: iterable of [1,3,H,W] tensors in [0,1] (host, ideally pinned); zoom_settings: one dict or one per image;
         consume(i, frames): called from the render thread with the uint8 [n,H,W,3] pinned tensor of image i;
+        trace: optional list that receives (image, stage, t_begin, t_end) host timestamps (perf_counter);
         -> list of those tensors (None entries when keep is False)."""
         import queue
         import threading
+        import time
         dev = torch.device(device)
+        # the two streams live with the Pipeline: the caching allocator keeps one pool per stream, and fresh streams would send
+        # the first image of every call through cudaMalloc again (measured: 90 ms instead of 21)
+        if getattr(self, '_streams', None) is None:
+            self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        s_cnn, s_render = self._streams
         images = list(images)
         zooms = zoom_settings if isinstance(zoom_settings, (list, tuple)) else [zoom_settings] * len(images)
         results = [None] * len(images)
@@ -186,14 +193,17 @@ class Pipeline():
         def render_loop():
             try:
                 torch.cuda.set_device(dev)
-                with torch.cuda.stream(torch.cuda.Stream(dev)):
+                with torch.cuda.stream(s_render):
                     while True:
                         item = q.get()
                         if item is None:
                             return
                         i, oc, settings, ready = item
+                        t0 = time.perf_counter()
                         torch.cuda.current_stream().wait_event(ready)
                         out = render_poses(settings, oc, kenburns_poses(settings, oc))      # synchronises its own stream only
+                        if trace is not None:
+                            trace.append((i, 'render', t0, time.perf_counter()))
                         if consume is not None:
                             consume(i, out)
                         if keep:
@@ -205,14 +215,18 @@ class Pipeline():
 
         th = threading.Thread(target=render_loop, daemon=True)
         th.start()
-        with torch.cuda.stream(torch.cuda.Stream(dev)):
+        s_cnn.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s_cnn):
             for i, img in enumerate(images):
                 settings = {'dblSteps': np.linspace(0.0, 1.0, self.frames).tolist(), 'objectFrom': zooms[i]['objectFrom'],
                             'objectTo': zooms[i]['objectTo'], 'boolInpaint': True, 'dolly': self.dolly}
+                t0 = time.perf_counter()
                 self.estimate_depth(img)
                 prepare_cloud(settings, self.objectCommon, self.moduleInpaint)
                 ready = torch.cuda.Event()
                 ready.record()
+                if trace is not None:
+                    trace.append((i, 'cnn', t0, time.perf_counter()))
                 q.put((i, dict(self.objectCommon), settings, ready))
                 if err:
                     break

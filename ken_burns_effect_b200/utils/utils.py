@@ -22,6 +22,27 @@ def resize_image(tensorImage, max_size=512):
     return F.interpolate(input=tensorImage, size=(new_h, new_w), mode='bilinear', align_corners=False)
 
 
+def image_to_tensor(numpyImage, pretrained_estim=False, device_=None):
+    """kbe.py:96-114 + :181 on the device: the uint8 [H,W,3] array cv2.imread returned -> the [1,3,H',W'] float tensor in [0,1]
+    kbe.py hands to Pipeline.__call__ (ToTensor, Normalize(.5,.5), crop to multiples of 4, (x+1)/2), bit-identical to the host
+    path (kbe.load_image) but with 3 bytes per pixel crossing PCIe instead of 12 and no float images built on the host."""
+    import ctypes
+    from .. import _native as nat
+    dev = torch.device(device_ or device)
+    if dev.type != 'cuda':
+        raise RuntimeError("image_to_tensor needs a CUDA device (there is no CPU fallback)")
+    src = torch.from_numpy(numpyImage)
+    if src.dtype != torch.uint8 or src.dim() != 3 or src.shape[2] != 3:
+        raise RuntimeError(f"image_to_tensor: expected uint8 [H,W,3], got {src.dtype} {tuple(src.shape)}")
+    H, W = src.shape[0], src.shape[1]
+    src = src.contiguous().to(dev, non_blocking=True)
+    out = torch.empty(1, 3, H - H % 4, W - W % 4, device=dev, dtype=torch.float32)
+    nat.check(nat.lib().kb_image_front_end(ctypes.c_void_p(src.data_ptr()), H, W, 1 if pretrained_estim else 0,
+                                           ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+              "kb_image_front_end")
+    return out
+
+
 def save_model(models_dict, nb_iter, path='models/trained'):
     for model_type, model in models_dict.items():
         payload = {'nb_iter': nb_iter, 'model_state_dict': model['model'].state_dict()}

@@ -210,3 +210,19 @@ def test_run_many_equals_one_image_at_a_time():
         assert d.shape == (4, H, W, 3)
         assert (d > 1).mean() <= max(1e-3, 3 * (noise > 1).mean()) and (d > 0).mean() <= max(5e-3, 3 * (noise > 0).mean()), \
             f"image {i}: {(d > 0).mean():.2e} of bytes differ ({(d > 1).mean():.2e} by more than 1); run-to-run noise {(noise > 0).mean():.2e}"
+
+
+def test_device_image_front_end_is_bit_identical_to_the_host_path(tmp_path):
+    """utils.image_to_tensor (kb_image_front_end: uint8 HWC -> ToTensor -> Normalize -> crop x4 -> (x+1)/2 on the device) against
+    kbe.load_image + (x + 1) / 2, the reference's host path (kbe.py:96-114, :181), for both channel orders and a size that crops."""
+    import cv2
+    import kbe
+    from ken_burns_effect_b200.utils.utils import image_to_tensor
+    img, _ = synthetic.synthetic_scene(387, 322, seed=21)
+    path = str(tmp_path / "in.png")
+    cv2.imwrite(path, img)
+    for flag in (False, True):
+        host = kbe.load_image(path, flag)
+        host = (host.view(1, 3, host.size(1), host.size(2)) + 1) / 2
+        dev = image_to_tensor(cv2.imread(path, cv2.IMREAD_COLOR), flag)
+        assert dev.shape == (1, 3, 320, 384) and torch.equal(dev.cpu(), host.contiguous())
