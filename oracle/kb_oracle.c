@@ -47,6 +47,20 @@ KBO_API int kbo_max_threads(void) {
 }
 
 /* ---- float atomics on plain memory (the reference's atomicMin is a CAS loop, common.py:275-283) ---- */
+/* Grow-only scratch buffers, one per slot: a frame needs ~75 MB of temporaries, and getting them from malloc() every frame means
+ * fresh mmaps and ~18 000 page faults per frame -- which made the SAME loop measure 36 frames/s in a fresh process and 55 in a
+ * process whose heap had been stretched before (bench.py's two arms).  Single caller at a time (the kernels inside are OpenMP). */
+static void *kbo_scratch(int slot, size_t bytes) {
+  static void *buf[16];
+  static size_t cap[16];
+  if (bytes > cap[slot]) {
+    free(buf[slot]);
+    buf[slot] = malloc(bytes);
+    cap[slot] = buf[slot] ? bytes : 0;
+  }
+  return buf[slot];
+}
+
 static inline void atomic_min_f32(float *addr, float v) {
   int32_t *ia = (int32_t *)addr;
   int32_t old = __atomic_load_n(ia, __ATOMIC_RELAXED);
@@ -289,11 +303,10 @@ KBO_API int kbo_render_pointcloud(const float *xyz, const float *data, int B, lo
                                   double focal, double baseline, int degrid_mode, float *render,
                                   float *existing, float *zee_raw, float *zee_out) {
   const long P = (long)H * W;
-  float *z0 = (float *)malloc(sizeof(float) * B * P);
-  float *z1 = (float *)malloc(sizeof(float) * B * P);
-  float *acc = (float *)malloc(sizeof(float) * B * (C + 1) * P);
+  float *z0 = (float *)kbo_scratch(0, sizeof(float) * B * P);
+  float *z1 = (float *)kbo_scratch(1, sizeof(float) * B * P);
+  float *acc = (float *)kbo_scratch(2, sizeof(float) * B * (C + 1) * P);
   if (!z0 || !z1 || !acc) {
-    free(z0); free(z1); free(acc);
     return -1;
   }
   kbo_splat_min(xyz, B, N, focal, baseline, z0, H, W, NULL);
@@ -302,7 +315,6 @@ KBO_API int kbo_render_pointcloud(const float *xyz, const float *data, int B, lo
   if (zee_out) memcpy(zee_out, z1, sizeof(float) * B * P);
   kbo_splat_accum(xyz, data, B, N, C, focal, baseline, z1, acc, H, W);
   kbo_normalize(acc, B, C, H, W, render, existing);
-  free(z0); free(z1); free(acc);
   return 0;
 }
 
@@ -485,12 +497,12 @@ KBO_API void kbo_resize_linear_8u3(const uint8_t *src, int sh, int sw, int dh, i
 KBO_API int kbo_frame(const float *xyz_shifted, const float *rgbd, long N, int W, int H, double focal,
                       double baseline, int crop_w, int crop_h, int degrid_mode, uint8_t *frame) {
   const long P = (long)H * W;
-  float *render = (float *)malloc(sizeof(float) * 4 * P);
-  float *existing = (float *)malloc(sizeof(float) * P);
-  float *dmask = (float *)malloc(sizeof(float) * P);
-  float *filled = (float *)malloc(sizeof(float) * 4 * P);
-  uint8_t *u8 = (uint8_t *)malloc(3 * P);
-  uint8_t *patch = (uint8_t *)malloc((size_t)3 * crop_w * crop_h);
+  float *render = (float *)kbo_scratch(3, sizeof(float) * 4 * P);
+  float *existing = (float *)kbo_scratch(4, sizeof(float) * P);
+  float *dmask = (float *)kbo_scratch(5, sizeof(float) * P);
+  float *filled = (float *)kbo_scratch(6, sizeof(float) * 4 * P);
+  uint8_t *u8 = (uint8_t *)kbo_scratch(7, 3 * P);
+  uint8_t *patch = (uint8_t *)kbo_scratch(8, (size_t)3 * crop_w * crop_h);
   if (!render || !existing || !dmask || !filled || !u8 || !patch) return -1;
   int rc = kbo_render_pointcloud(xyz_shifted, rgbd, 1, N, 4, W, H, focal, baseline, degrid_mode, render,
                                  existing, NULL, NULL);
@@ -500,7 +512,6 @@ KBO_API int kbo_frame(const float *xyz_shifted, const float *rgbd, long N, int W
   kbo_to_uint8(filled, H, W, u8);
   kbo_getrectsubpix_8u3(u8, H, W, crop_w, crop_h, W / 2.0, H / 2.0, patch);
   kbo_resize_linear_8u3(patch, crop_h, crop_w, H, W, frame);
-  free(render); free(existing); free(dmask); free(filled); free(u8); free(patch);
   return rc;
 }
 

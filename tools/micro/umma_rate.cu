@@ -64,6 +64,76 @@ __global__ void k(int N, int nacc, int reps, uint32_t sbo, int a_off, long long 
   if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512) : "memory");
 }
 
+// Conv-like pattern: 36 MMAs per "tile" (9 taps x 4 k-steps of a 32-channel chunk) with the operand addresses of the persistent
+// halo kernel (A: tap row/column offsets into a 10 x 18 pixel halo tile of 128-byte rows, SBO = 1280; B: 36 distinct 32-byte
+// slices of 9 resident 4 KB panels), accumulating into one TMEM accumulator per tile, 4 accumulators in rotation.
+// bg: 0 none, 1 eight other warps stream 128-bit shared-memory LOADS (the epilogue's bias / slope tables), 2 they stream 128-bit
+// shared-memory STORES into an unrelated region (stand-in for TMA writes of the next halo tiles).
+template <int KIND>
+__global__ void kconv(int N, int tiles, int bg, long long *out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  __shared__ volatile int stop;
+  for (int i = threadIdx.x; i < (128 * 1024) / 4; i += blockDim.x) ((uint32_t *)smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    stop = 0;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tm = slot;
+  if (threadIdx.x == 0) {
+    const uint32_t fmt = KIND == 0 ? 2u : 1u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
+    const uint32_t a = smem_u32(smem), b = smem_u32(smem) + 32768;
+    uint64_t da[36], db[36];
+    for (int tap = 0; tap < 9; ++tap)
+      for (int k = 0; k < 4; ++k) {
+        da[tap * 4 + k] = desc_sw128(a + ((tap / 3) * 10 + (tap % 3)) * 128 + k * 32, 1280);
+        db[tap * 4 + k] = desc_sw128(b + tap * 4096 + k * 32, 1024);
+      }
+    long long t0 = clock64();
+    for (int t = 0; t < tiles; ++t) {
+      const uint32_t d = tm + (uint32_t)((t & 3) * N);
+#pragma unroll
+      for (int i = 0; i < 36; ++i) mma<KIND>(d, da[i], db[i], idesc, i != 0);
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile("{\n.reg .pred p;\nW2:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra D2;\nbra W2;\nD2:\n}" ::"r"(smem_u32(&bar)) : "memory");
+    long long t1 = clock64();
+    stop = 1;
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  } else if (threadIdx.x >= 64 && bg) {
+    // background traffic on [80 KB, 128 KB): away from the operands
+    uint4 *reg = (uint4 *)(smem + 80 * 1024);
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    int i = threadIdx.x - 64;
+    while (!stop) {
+      if (bg == 1) {
+        uint4 v = reg[i & 2047];
+        acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+      } else {
+        reg[i & 2047] = acc;
+        acc.x += 1;
+      }
+      i += 256;
+    }
+    if (acc.x == 0x12345678u) out[1] = acc.y;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512) : "memory");
+}
+
 int main() {
   long long *out;
   cudaMallocManaged(&out, 8);
@@ -86,6 +156,22 @@ int main() {
           printf("{\"kind\": \"%s\", \"N\": %d, \"accumulators\": %d, \"halo_desc\": %d, \"cycles_per_mma\": %.1f, \"floor\": %d}\n",
                  kind ? "bf16" : "tf32", N, nacc, variant, (double)out[0] / reps, N / 2);
         }
+      }
+  cudaFuncSetAttribute(kconv<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
+  cudaFuncSetAttribute(kconv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
+  for (int kind = 0; kind < 2; ++kind)
+    for (int N : {32, 64})
+      for (int bg = 0; bg < 3; ++bg) {
+        const int tiles = 128;
+        for (int it = 0; it < 2; ++it) {
+          if (kind == 0) kconv<0><<<148, 320, 132 * 1024>>>(N, tiles, bg, out);
+          else kconv<1><<<148, 320, 132 * 1024>>>(N, tiles, bg, out);
+          cudaError_t e = cudaDeviceSynchronize();
+          if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+        }
+        printf("{\"pattern\": \"conv 9 taps x 4 k-steps, 36 MMAs per accumulator\", \"kind\": \"%s\", \"N\": %d, \"background\": \"%s\", \"cycles_per_mma\": %.1f}\n",
+               kind ? "bf16" : "tf32", N, bg == 0 ? "none" : (bg == 1 ? "8 warps of 128-bit shared loads" : "8 warps of 128-bit shared stores"),
+               (double)out[0] / (tiles * 36));
       }
   return 0;
 }
