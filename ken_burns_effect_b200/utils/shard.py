@@ -105,54 +105,118 @@ def broadcast_cloud(objectCommon, device, src=0, group=None):
 
 
 class CloudExchange:
-    """The exchange step without a stream drain: a preallocated receive buffer, the 128-byte header on a HOST side channel
+    """The exchange step without a stream drain: preallocated receive buffers, the 128-byte header on a HOST side channel
     (a gloo group: the non-source ranks learn N without reading anything back from their GPU, so the kernels of the previous
-    effect keep running while the host already posts the next broadcast), then ONE broadcast of exactly 28*N payload bytes
-    into the buffer.  On the source rank the cloud is sent from where it lies when it is already packed ([7,N] contiguous,
+    effect keep running while the host already posts the next broadcast), then ONE broadcast of exactly 28*N payload bytes.
+    On the source rank the cloud is sent from where it lies when it is already packed ([7,N] contiguous,
     objectCommon['tensorPacked']), else three device copies place it in the buffer (no torch.cat, no fresh allocation).
+
+    On CUDA the broadcast runs on its own stream into one of TWO buffers, so the cloud of effect i+1 can travel while effect i
+    still renders out of the other buffer (broadcast_async + wait(cloud) where the cloud is first read; broadcast() = both at
+    once).  Call consumed(cloud) after enqueuing the work that reads a cloud: its buffer is rewritten only after that mark.
     """
 
     def __init__(self, device, capacity_points, src=0, group=None):
-        self.device, self.src, self.group = device, src, group
-        self.buf = torch.empty(7 * int(capacity_points), dtype=torch.float32, device=device)
+        self.device, self.src, self.group = torch.device(device), src, group
+        self.cuda = self.device.type == 'cuda'
+        nbuf = 2 if self.cuda else 1
+        self.bufs = [torch.empty(7 * int(capacity_points), dtype=torch.float32, device=device) for _ in range(nbuf)]
+        self.slot = 0
+        self.stream = torch.cuda.Stream(self.device) if self.cuda else None
+        self.read_done = [None] * nbuf                     # event: the last reader of this buffer has been enqueued and passed
+        self.in_use = [False] * nbuf                       # broadcast into, not yet marked consumed
         self.host_group = None
         rank, R = world()
         if R > 1:
             backend = dist.get_backend(group)
             self.host_group = group if backend == 'gloo' else dist.new_group(backend='gloo')
 
-    def _fit(self, n):
-        if 7 * n > self.buf.numel():                       # rare: a cloud larger than promised -- grow once, keep it
-            self.buf = torch.empty(7 * n, dtype=torch.float32, device=self.device)
+    @property
+    def buf(self):
+        return self.bufs[0]
+
+    def _fit(self, slot, n):
+        if 7 * n > self.bufs[slot].numel():                # rare: a cloud larger than promised -- grow once, keep it
+            self.bufs[slot] = torch.empty(7 * n, dtype=torch.float32, device=self.device)
+
+    def consumed(self, cloud):
+        """Mark on the current stream: everything enqueued so far has finished reading `cloud` (a result of broadcast*)."""
+        slot = cloud.get('_slot')
+        if self.cuda and slot is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self.read_done[slot] = ev
+            self.in_use[slot] = False
+
+    def wait(self, cloud):
+        """Make the current stream wait for the arrival of `cloud` (needed once, before its first reader, after broadcast_async)."""
+        ev = cloud.get('_ready')
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+        return cloud
 
     def broadcast(self, objectCommon):
-        """objectCommon: read on the source rank only (None elsewhere) -> the unpacked cloud on every rank."""
+        """objectCommon: read on the source rank only (None elsewhere) -> the unpacked cloud on every rank, ordered before
+        everything enqueued on the current stream afterwards."""
+        return self.wait(self.broadcast_async(objectCommon))
+
+    def broadcast_async(self, objectCommon):
+        """Like broadcast(), but the current stream does not wait: call wait(cloud) where the cloud is first read."""
         rank, R = world()
         if R == 1:
             packed, hdr = pack_cloud(objectCommon)
             return unpack_cloud(packed.to(self.device), hdr)
+        slot = self.slot
+        self.slot = (self.slot + 1) % len(self.bufs)
         hdr = torch.zeros(HEADER_DOUBLES, dtype=torch.float64)
         send = None
+        main = torch.cuda.current_stream(self.device) if self.cuda else None
+        if self.cuda:
+            if self.in_use[slot] or self.read_done[slot] is None:
+                self.stream.wait_stream(main)                           # the reader never marked (or first use): stream order
+            else:
+                self.stream.wait_event(self.read_done[slot])           # the previous content of this buffer is no longer read
         if rank == self.src:
             hdr = cloud_header(objectCommon)
             n = int(hdr[0])
             pk = objectCommon.get('tensorPacked')
-            if pk is not None and pk.is_contiguous() and tuple(pk.shape) == (7, n) and pk.device == self.buf.device:
+            if pk is not None and pk.is_contiguous() and tuple(pk.shape) == (7, n) and pk.device == self.bufs[slot].device:
                 send = pk.view(-1)
+                if self.cuda:
+                    self.stream.wait_stream(main)                       # whatever produced the packed cloud
             else:
-                self._fit(n)
-                send = self.buf[:7 * n]
+                self._fit(slot, n)
+                send = self.bufs[slot][:7 * n]
                 v = send.view(7, n)
-                v[0:3].copy_(objectCommon['tensorInpaPoints'].reshape(3, n))
-                v[3:6].copy_(objectCommon['tensorInpaImage'].reshape(3, n))
-                v[6:7].copy_(objectCommon['tensorInpaDepth'].reshape(1, n))
+                if self.cuda:
+                    self.stream.wait_stream(main)                       # stage A produced the tensors on the caller's stream
+                with (torch.cuda.stream(self.stream) if self.cuda else _null()):
+                    v[0:3].copy_(objectCommon['tensorInpaPoints'].reshape(3, n))
+                    v[3:6].copy_(objectCommon['tensorInpaImage'].reshape(3, n))
+                    v[6:7].copy_(objectCommon['tensorInpaDepth'].reshape(1, n))
         dist.broadcast(hdr, src=self.src, group=self.host_group)            # host to host: no GPU involved
         n = int(hdr[0])
         if rank != self.src:
-            self._fit(n)
-            send = self.buf[:7 * n]
-        dist.broadcast(send, src=self.src, group=self.group)                # 28 * N bytes over NVLink, stream-ordered
-        return unpack_cloud(send.view(7, n), hdr)
+            self._fit(slot, n)
+            send = self.bufs[slot][:7 * n]
+        with (torch.cuda.stream(self.stream) if self.cuda else _null()):
+            dist.broadcast(send, src=self.src, group=self.group)            # 28 * N bytes over NVLink, on the exchange stream
+        cloud = unpack_cloud(send.view(7, n), hdr)
+        cloud['_slot'] = slot
+        cloud['_ready'] = None
+        if self.cuda:
+            cloud['_ready'] = torch.cuda.Event()
+            cloud['_ready'].record(self.stream)
+            self.in_use[slot] = True
+        return cloud
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 class SharedFrames:
