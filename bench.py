@@ -233,6 +233,7 @@ def config3_4k(rank, world, dev, frames=300, steps=3, warmup=2):
             c = xchg.broadcast(cloud0)
             r.set_cloud(c['tensorInpaPoints'], c['tensorInpaImage'], c['tensorInpaDepth'])
             r.render_into(poses, dst)
+            xchg.consumed(c)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:

@@ -149,6 +149,7 @@ class Pipeline():
             sink = FrameSink(output_path, len(mine), write_frames=True, write_video=False, rgb_to_bgr=pretrained_estim,
                              frame_indices=mine, t0=t_start)
         render_poses(settings, cloud, [poses[i] for i in mine], sink=sink, out=shared.block())
+        ex.consumed(cloud)
         mark('t_own_frames_in_host_memory_s')
         torch.distributed.barrier()                      # every block of the shared segment is complete
         numpyResult = [shared.frame(i) for i in range(len(poses))]
