@@ -21,9 +21,6 @@ from .. import _native as nat
 # batch by batch on a second stream and overlap better in batches of 16 (end to end 19.7 k vs 18.6 k frames/s).
 FRAME_BATCH = 32
 FRAME_BATCH_TO_HOST = 16
-# Launch groups in flight (workspaces x streams) inside FrameRenderer.render_into; KB200_RENDER_STREAMS overrides.
-import os as _os
-RENDER_STREAMS = int(_os.environ.get("KB200_RENDER_STREAMS", "1"))
 
 
 def _stream():
@@ -392,13 +389,9 @@ class FrameRenderer:
         self.params = nat.KBFrameParams(self.H, self.W, int(crop_w), int(crop_h), float(dblBaseline))
         L = nat.lib()
         nbytes = L.kb_frames_workspace_bytes(ctypes.byref(self.params), self.batch)
-        # RENDER_STREAMS launch groups in flight: consecutive groups of poses alternate between that many workspaces and streams, so
-        # the tail of one group's kernels overlaps the head of the next group's (measured: profiles/, bench r02s)
-        self.n_lanes = max(1, int(RENDER_STREAMS))
-        self.ws = [torch.empty(nbytes + 256, device=self.device, dtype=torch.uint8) for _ in range(self.n_lanes)]
-        self.ws_ptrs = [w.data_ptr() + ((-w.data_ptr()) % 256) for w in self.ws]
-        self.ws_ptr = self.ws_ptrs[0]
-        self.lanes = [torch.cuda.Stream(device=self.device) for _ in range(self.n_lanes)] if self.n_lanes > 1 else []
+        self.ws = torch.empty(nbytes + 256, device=self.device, dtype=torch.uint8)
+        off = (-self.ws.data_ptr()) % 256
+        self.ws_ptr = self.ws.data_ptr() + off
         # host destinations: two device staging buffers + a copy stream, so the D2H of batch i overlaps the
         # kernels of batch i+1 (2.36 MB per 1024x768 frame: PCIe is the end-to-end bound)
         self.dev_frames = [torch.empty(self.batch, self.H, self.W, 3, device=self.device, dtype=torch.uint8) for _ in range(2)]
@@ -431,8 +424,6 @@ class FrameRenderer:
         main = torch.cuda.current_stream(self.device)
         to_host = not out_frames.is_cuda
         it = 0
-        for ls in self.lanes:
-            ls.wait_stream(main)                                # the cloud (set_cloud, broadcast) is ready on the caller's stream
         while done < n:
             k = min(self.batch if not to_host else min(self.batch, FRAME_BATCH_TO_HOST), n - done)
             arr = (nat.KBPose * k)()
@@ -442,19 +433,16 @@ class FrameRenderer:
                 arr[i].focal = float(focal)
             dst = out_frames[done:done + k]
             slot = it & 1
-            lane = it % self.n_lanes
-            rs = self.lanes[lane] if self.lanes else main        # the stream this group renders on
             if to_host:
                 if it >= 2:
-                    rs.wait_event(self.ev_copied[slot])          # staging buffer free again
+                    main.wait_event(self.ev_copied[slot])        # staging buffer free again
                 target = self.dev_frames[slot][:k]
             else:
                 target = dst
             nat.check(L.kb_render_frames(_ptr(self.xyz), _ptr(self.rgbd), self.N, arr, k, ctypes.byref(self.params),
-                                         ctypes.c_void_p(self.ws_ptrs[lane]), _ptr(target), ctypes.c_void_p(rs.cuda_stream)),
-                      "kb_render_frames")
+                                         ctypes.c_void_p(self.ws_ptr), _ptr(target), _stream()), "kb_render_frames")
             if to_host:
-                self.ev_rendered[slot].record(rs)
+                self.ev_rendered[slot].record(main)
                 self.copy_stream.wait_event(self.ev_rendered[slot])
                 with torch.cuda.stream(self.copy_stream):
                     dst.copy_(target, non_blocking=True)
@@ -465,12 +453,10 @@ class FrameRenderer:
                         on_batch(done, k, ev)
             elif on_batch is not None:
                 ev = torch.cuda.Event()
-                ev.record(rs)
+                ev.record(main)
                 on_batch(done, k, ev)
             done += k
             it += 1
-        for ls in self.lanes:
-            main.wait_stream(ls)
         if to_host:
             main.wait_stream(self.copy_stream)                   # the caller's sync on the current stream covers the copies
         return out_frames
