@@ -139,6 +139,9 @@ def _max_over_ranks(ms, world, dev):
     return float(t.item())
 
 
+DEPTH_BATCH = 4      # images whose depth stage runs as one batched forward in throughput mode (Pipeline.estimate_depth_batch)
+
+
 def throughput_mode(rank, world, dev, images_per_gpu=8, frames=150):
     """BASELINE configs[4]: a batch of images (64 at 8 GPUs), one full 150-frame KBE each, IMAGES sharded over the GPUs: every rank
     runs the whole pipeline (depth CNNs, two inpainting passes, render loop, frames into pinned host memory) on its own images --
@@ -166,7 +169,8 @@ def throughput_mode(rank, world, dev, images_per_gpu=8, frames=150):
 
     for t in imgs[:4]:                      # warm-up: weight packing, CUDA-graph capture of the forwards, pinned pool
         one(t)
-    pipe.run_many(imgs[:2], zoom, keep=False)
+    for _ in range(3):
+        pipe.run_many(imgs[:DEPTH_BATCH], zoom, keep=False, depth_batch=DEPTH_BATCH)   # incl. graph capture at batch size
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -178,7 +182,7 @@ def throughput_mode(rank, world, dev, images_per_gpu=8, frames=150):
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    pipe.run_many(imgs, zoom, keep=False)   # (b) Pipeline.run_many: CNN stage of image i+1 overlaps the frame loop of image i
+    pipe.run_many(imgs, zoom, keep=False, depth_batch=DEPTH_BATCH)   # (b) Pipeline.run_many: batched depth stage, CNN stage of image i+1 overlaps the frame loop of image i
     torch.cuda.synchronize()
     ms = 1e3 * (time.perf_counter() - t0)
     if world > 1:
@@ -187,7 +191,7 @@ def throughput_mode(rank, world, dev, images_per_gpu=8, frames=150):
     ms_serial = _max_over_ranks(ms_serial, world, dev)
     n_img = images_per_gpu * world
     return {"what": f"configs[4]: {n_img} images of 1024x768, one {frames}-frame KBE each, {images_per_gpu} images per GPU, full pipeline "
-                    "per rank (image in pinned host memory -> frames in pinned host memory), TF32 tcgen05 convolutions",
+                    f"per rank (image in pinned host memory -> frames in pinned host memory), TF32 tcgen05 convolutions, depth stage in batches of {DEPTH_BATCH}",
             "images_per_s": n_img / (ms / 1e3), "frames_per_s": n_img * frames / (ms / 1e3), "ms_per_image_per_gpu": ms / images_per_gpu,
             "one_image_at_a_time": {"images_per_s": n_img / (ms_serial / 1e3), "ms_per_image_per_gpu": ms_serial / images_per_gpu},
             "images": n_img, "dtype_cnn": "tf32", "weights": "random-init (no checkpoints offline)"}

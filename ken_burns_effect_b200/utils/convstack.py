@@ -323,10 +323,16 @@ def graphed(owner, tag, fn, *tensors):
     if store is None:
         store = {}
         object.__setattr__(owner, '_kb_graphs', store)
-    sig = (tuple((tuple(t.shape), t.dtype, t.device.index) for t in tensors), _fingerprint(owner))
-    ent = store.get(tag)
+    shapes = tuple((tuple(t.shape), t.dtype, t.device.index) for t in tensors)
+    sig = (shapes, _fingerprint(owner))
+    # one graph per (forward, input shapes): a pipeline that alternates batch sizes (estimate_depth_batch next to single images)
+    # keeps both; a change of the owner's parameters drops every graph of that forward
+    ent = store.get((tag, shapes))
     if ent is None or ent['sig'] != sig:
-        ent = store[tag] = {'sig': sig, 'graph': None, 'calls': 0}
+        if ent is not None:
+            for k in [k for k in store if k[0] == tag]:
+                del store[k]
+        ent = store[(tag, shapes)] = {'sig': sig, 'graph': None, 'calls': 0}
     if ent['graph'] is None:
         ent['calls'] += 1
         if ent['calls'] <= GRAPH_EAGER_CALLS:

@@ -77,6 +77,38 @@ class Pipeline():
         return oc
 
     @torch.no_grad()
+    def estimate_depth_batch(self, tensorImages):
+        """The one-time depth stage (pipeline.py:61-100) for B images of one size at once: Semantics, Disparity and Refine run ONE
+        forward with batch B (the reference asserts B == 1, pipeline.py:63; its modules are batch-generic and so are the tcgen05
+        executors) -- the 24x32 ... 6x8 maps of the Disparity GridNet then fill the GPU -- followed by the per-image normalisation.
+        -> list of B objectCommon dicts, each what estimate_depth() leaves for that image alone (the convolutions work image by
+        image; torch's per-sample mean / std reductions sum a [B, n] tensor in another order than a [1, n] one, so the result
+        agrees to fp32 reassociation noise, ~1e-6, not bit for bit)."""
+        base = self.objectCommon
+        imgs = tensorImages.to(device).contiguous()
+        B, _, H, W = imgs.shape
+        resized = resize_image(imgs, max_size=int(max(W, H) / 2))
+        disparity = self.moduleDisparity(resized, self.moduleSemantics(resized))
+        if self.d2:
+            disparity = torch.ones_like(disparity)
+        disparity = self.moduleRefine(imgs, disparity)
+        lo = disparity.reshape(B, -1).min(1)[0].view(B, 1, 1, 1)
+        disparity = torch.where(lo < 0.0, disparity - lo, disparity)                      # pipeline.py:79-80, per image
+        disparity = disparity / disparity.reshape(B, -1).max(1)[0].view(B, 1, 1, 1) * base['dblBaseline']
+        depth = (base['dblFocal'] * base['dblBaseline']) / (disparity + 1e-7)
+        points = depth_to_points(depth, base['dblFocal'])
+        crop = depth[:, 0, 128:-128, 128:-128].detach().cpu().numpy()                    # one D2H for the batch
+        dmin = disparity.reshape(B, -1).min(1)[0].tolist()
+        dmax = disparity.reshape(B, -1).max(1)[0].tolist()
+        out = []
+        for b in range(B):
+            out.append({'dblFocal': base['dblFocal'], 'dblBaseline': base['dblBaseline'], 'intWidth': W, 'intHeight': H,
+                        'dblDispmin': dmin[b], 'dblDispmax': dmax[b], 'objectDepthrange': cv2.minMaxLoc(src=crop[b], mask=None),
+                        'tensorRawPoints': points[b:b + 1].view(1, 3, -1), 'tensorRawImage': imgs[b:b + 1],
+                        'tensorRawDisparity': disparity[b:b + 1], 'tensorRawDepth': depth[b:b + 1]})
+        return out
+
+    @torch.no_grad()
     def __call__(self, tensorImage, zoom_settings, output_path=None, inpaint_depth=False, pretrained_estim=False):
         """-> list of uint8 [H,W,3] frames (every rank gets the whole list under torchrun).  With output_path the frames go to an
         asynchronous sink (utils/sink.py) while they render: <out>/frames/<i>.png when output_frames, <out>/3d_kbe.mp4 always --
@@ -165,7 +197,7 @@ class Pipeline():
 
 
     @torch.no_grad()
-    def run_many(self, images, zoom_settings, consume=None, keep=True, trace=None):
+    def run_many(self, images, zoom_settings, consume=None, keep=True, trace=None, depth_batch=1):
         """Throughput mode (BASELINE configs[4]: many images, one effect each, per GPU): the same stages as __call__, software-
         pipelined over the images on two CUDA streams -- the CNN stage of image i+1 (tensor-core bound: depth networks + two
         inpainting passes) runs on one stream while a helper thread renders the frames of image i on another (HBM / PCIe bound:
@@ -174,6 +206,7 @@ class Pipeline():
 
         images: iterable of [1,3,H,W] tensors in [0,1] (host, ideally pinned); zoom_settings: one dict or one per image;
         consume(i, frames): called from the render thread with the uint8 [n,H,W,3] pinned tensor of image i;
+        depth_batch: images whose depth stage runs as one batched forward (estimate_depth_batch; same size required);
         trace: optional list that receives (image, stage, t_begin, t_end) host timestamps (perf_counter);
         -> list of those tensors (None entries when keep is False)."""
         import queue
@@ -218,17 +251,26 @@ class Pipeline():
         th.start()
         s_cnn.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(s_cnn):
+            depth_batch = max(1, int(depth_batch))
+            ahead = []                                   # objectCommon dicts of the current depth batch, in order
             for i, img in enumerate(images):
                 settings = {'dblSteps': np.linspace(0.0, 1.0, self.frames).tolist(), 'objectFrom': zooms[i]['objectFrom'],
                             'objectTo': zooms[i]['objectTo'], 'boolInpaint': True, 'dolly': self.dolly}
                 t0 = time.perf_counter()
-                self.estimate_depth(img)
-                prepare_cloud(settings, self.objectCommon, self.moduleInpaint)
+                if depth_batch == 1:
+                    self.estimate_depth(img)
+                    oc = self.objectCommon
+                else:
+                    if not ahead:
+                        chunk = images[i:i + depth_batch]
+                        ahead = self.estimate_depth_batch(torch.cat([c.to(device, non_blocking=True) for c in chunk], 0))
+                    oc = ahead.pop(0)
+                prepare_cloud(settings, oc, self.moduleInpaint)
                 ready = torch.cuda.Event()
                 ready.record()
                 if trace is not None:
                     trace.append((i, 'cnn', t0, time.perf_counter()))
-                q.put((i, dict(self.objectCommon), settings, ready))
+                q.put((i, dict(oc), settings, ready))
                 if err:
                     break
         q.put(None)
