@@ -125,7 +125,7 @@ def full_pipeline(steps=3, warmup=3, frames=150):
     total = t_cnn + t_render
     return {"value": frames * steps / total, "unit": "frames/s", "ms_per_kbe": 1e3 * total / steps,
             "ms_cnn_and_inpaint_stage": 1e3 * t_cnn / steps, "ms_render_loop": 1e3 * t_render / steps, "points": int(npts),
-            "conv_tflop_per_kbe": 2.30, "note": "random-init weights: the disparity is noise-like, so the appended point "
+            "conv_tflop_per_kbe": 2.30, "dtype_cnn": "tf32 (tcgen05 kind::tf32, fp32 accumulate; the render loop is f32)", "note": "random-init weights: the disparity is noise-like, so the appended point "
             "count and hole statistics are not those of a trained model; CNN forwards replay from CUDA graphs from their 4th call on (captured during warm-up)"}
 
 

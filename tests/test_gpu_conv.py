@@ -159,27 +159,41 @@ def T(k):
     return torch.from_numpy(G[k]).cuda()
 
 
+NETWORK_BAR = 3.5e-3   # rel. L2 of a whole network on TF32 tensor cores vs the reference module in fp32; measured 0.8e-3 .. 2.3e-3
+#                        (profiles/conv_golden_rel_l2_r02.json; at 1024x768 against the reference on the same GPU: 2.3e-3,
+#                        profiles/parity_reference_e2e_r02*.json) -- the bar is the largest measured value + 50 % (round 1: 1e-2)
+
+
 def test_networks_vs_reference_goldens():
+    import json
+    import os
     from ken_burns_effect_b200.models.disparity_estimation import Disparity, Semantics
     from ken_burns_effect_b200.models.disparity_refinement import Refine
     from ken_burns_effect_b200.models.disparity_refinement_pretrained import Refine as RefineP
     from ken_burns_effect_b200.models.pointcloud_inpainting import Inpaint
+    vals = {}
     sem = kb_helpers.deterministic_state(Semantics().eval()).cuda()
     dis = kb_helpers.deterministic_state(Disparity().eval()).cuda()
     s = sem(T("net_img"))
-    assert rel(s, T("net_semantics")) < 1e-2
-    assert rel(dis(T("net_img"), T("net_semantics")), T("net_disparity")) < 1e-2
-    assert rel(kb_helpers.deterministic_state(Refine().eval()).cuda()(T("ref_img"), T("ref_disp_lo")), T("ref_refine")) < 1e-2
-    assert rel(kb_helpers.deterministic_state(RefineP().eval()).cuda()(T("ref_img"), T("ref_disp_lo")),
-               T("ref_refine_pretrained")) < 1e-2
+    vals["semantics"] = rel(s, T("net_semantics"))
+    vals["disparity"] = rel(dis(T("net_img"), T("net_semantics")), T("net_disparity"))
+    vals["refine"] = rel(kb_helpers.deterministic_state(Refine().eval()).cuda()(T("ref_img"), T("ref_disp_lo")), T("ref_refine"))
+    vals["refine_pretrained"] = rel(kb_helpers.deterministic_state(RefineP().eval()).cuda()(T("ref_img"), T("ref_disp_lo")),
+                                    T("ref_refine_pretrained"))
     net = kb_helpers.deterministic_state(Inpaint().eval()).cuda()
     mask = T("inp_mask")
     o = net(mask, tensorImage=T("ref_img") * mask, tensorDisparity=T("inp_disp") * mask)
     for k in ("tensorExisting", "tensorImage", "tensorDisparity"):
-        assert rel(o[k], T(f"inpaint_{k}")) < 1e-2, k
+        vals[f"inpaint_{k}"] = rel(o[k], T(f"inpaint_{k}"))
     from ken_burns_effect_b200.models.partial_inpainting import Inpaint as PartialInpaint
     net = kb_helpers.deterministic_state(PartialInpaint().eval()).cuda()
     o = net(mask, tensorImage=T("ref_img") * mask, tensorDisparity=T("inp_disp") * mask)
     assert torch.equal(o["tensorExisting"], T("partial_tensorExisting"))          # masks are exact
     for k in ("tensorImage", "tensorDisparity"):
-        assert rel(o[k], T(f"partial_{k}")) < 1e-2, k
+        vals[f"partial_{k}"] = rel(o[k], T(f"partial_{k}"))
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "conv_golden_rel_l2.json"), "w") as f:
+        json.dump(vals, f, indent=1)
+    for k, v in vals.items():
+        assert v < NETWORK_BAR, (k, v, vals)
