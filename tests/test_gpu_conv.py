@@ -161,7 +161,7 @@ def T(k):
 
 NETWORK_BAR = 3.5e-3   # rel. L2 of a whole network on TF32 tensor cores vs the reference module in fp32; measured 0.8e-3 .. 2.3e-3
 #                        (profiles/conv_golden_rel_l2_r02.json; at 1024x768 against the reference on the same GPU: 2.3e-3,
-#                        profiles/parity_reference_e2e_r02*.json) -- the bar is the largest measured value + 50 % (round 1: 1e-2)
+#                        profiles/parity_reference_e2e_r02u.json) -- the bar is the largest measured value + 50 % (round 1: 1e-2)
 
 
 def test_networks_vs_reference_goldens():

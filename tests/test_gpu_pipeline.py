@@ -257,3 +257,43 @@ def test_batched_depth_stage_equals_one_image_at_a_time():
     for x, y in zip(a, b):
         d = np.abs(x.numpy().astype(np.int16) - y.numpy().astype(np.int16))
         assert (d > 1).mean() < 1e-3 and (d > 0).mean() < 5e-3
+
+
+def test_pipeline_inpaint_depth_uses_the_second_network_for_disparity(tmp_path):
+    """kbe.py --inpaint-depth: four checkpoints, colour (and the existing-mask) from the first inpainting network, disparity from
+    the second (what the reference's list branch sets out to do, utils/common.py:50-62, pipeline.py:102-109)."""
+    from ken_burns_effect_b200.models.disparity_estimation import Disparity
+    from ken_burns_effect_b200.models.disparity_refinement import Refine
+    from ken_burns_effect_b200.models.pointcloud_inpainting import Inpaint
+    torch.manual_seed(8)
+    paths = []
+    for i, net in enumerate((Disparity(), Refine(), Inpaint(), Inpaint())):
+        p = str(tmp_path / f"m{i}.tar")
+        torch.save({'nb_iter': 0, 'model_state_dict': net.state_dict()}, p)
+        paths.append(p)
+    W, H = 384, 320
+    img, _ = synthetic.synthetic_scene(W, H, seed=41)
+    t = torch.from_numpy(img).permute(2, 0, 1).contiguous().float().div(255).view(1, 3, H, W)
+    pipe = Pipeline(model_paths=paths, dolly=False, frames=2)
+    seen = {0: [], 1: []}
+    for idx, net in enumerate((pipe.moduleInpaint, pipe.moduleInpaintDepth)):
+        orig = net.pointcloud_inpainting
+
+        def spy(*a, _orig=orig, _idx=idx, **k):
+            out = _orig(*a, **k)
+            seen[_idx].append({key: v.clone() for key, v in out.items()})
+            return out
+        net.pointcloud_inpainting = spy
+    frames = pipe(t, synthetic.default_zoom(W, H), inpaint_depth=True)
+    assert len(frames) == 2 and len(seen[0]) == 2 and len(seen[1]) == 2
+    oc = pipe.objectCommon
+    start = W * H
+    for colour, depth in zip(seen[0], seen[1]):
+        idx = (colour['tensorExisting'].view(-1) == 0).nonzero()[:, 0]
+        stop = start + idx.numel()
+        assert torch.equal(oc['tensorInpaImage'][0, :, start:stop], colour['tensorImage'].view(3, -1)[:, idx])
+        assert torch.equal(oc['tensorInpaDisparity'][0, :, start:stop], depth['tensorDisparity'].view(1, -1)[:, idx])
+        start = stop
+    assert start == oc['tensorInpaPoints'].shape[-1]
+    with pytest.raises(ValueError):
+        Pipeline(model_paths=paths[:3], dolly=False, frames=2)(t, synthetic.default_zoom(W, H), inpaint_depth=True)
