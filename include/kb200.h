@@ -158,6 +158,11 @@ long kb_conv_packed_floats(int Cout, int Cin, int ksize);
 int kb_conv_pack_weights(const float *w_oihw, int Cout, int Cin, int ksize, const float *out_scale, float *packed,
                          kb_stream_t stream);
 
+/* The same filters as fp16 panels for kb_conv_args.x_f16 (halves: kb_conv_packed_halves). */
+long kb_conv_packed_halves(int Cout, int Cin, int ksize);
+int kb_conv_pack_weights_f16(const float *w_oihw, int Cout, int Cin, int ksize, const float *out_scale, void *packed,
+                             kb_stream_t stream);
+
 typedef struct kb_conv_out {
   float *ptr;            /* [N,Ho,Wo,pixel_stride] */
   long pixel_stride;     /* floats, multiple of 4, >= round_up(Cout,4); channels Cout..round_up(Cout,4) are written as 0 */
@@ -166,7 +171,8 @@ typedef struct kb_conv_out {
   const float *mul;      /* optional [N,Ho,Wo] per-pixel factor applied last: the {0,1} mask a PartialConv2d consumer multiplies
                             its input with (utils/partial_conv.py:71: conv(input * mask)) */
   int round_tf32;        /* 1: round to TF32 (value is only ever read by another convolution) */
-  int _pad;
+  int store_f16;         /* 1: store as fp16 (ptr points at halves, pixel_stride counts halves, multiple of 8): the value is the
+                            input of a kind::f16 convolution (x_f16 below); saturated to +-65504 */
 } kb_conv_out;
 
 typedef struct kb_conv_args {
@@ -188,6 +194,9 @@ typedef struct kb_conv_args {
   int n_block;           /* 0 = auto; output channels per CTA (multiple of 16, <= 256) */
   int stages;            /* 0 = auto; shared-memory pipeline depth */
   int algo;              /* 0 = auto; 1 = one TMA load per filter tap (any filter); 2 = persistent halo kernel (stride 1, k <= 3) */
+  int x_f16;             /* 1: x holds fp16 (x_stride counts halves, multiple of 8) and w_packed comes from kb_conv_pack_weights_f16:
+                            tcgen05 kind::f16 -- the same 10 mantissa bits the TF32 path keeps of its operands, twice the MACs per
+                            MMA and half the operand bytes; accumulation, bias, residual and un-flagged outputs stay fp32 */
 } kb_conv_args;
 
 /* out_o = prelu_o(pc(conv(x, w) + bias) + res) * mul_o   for o < n_out;  one launch. */
@@ -196,8 +205,8 @@ int kb_conv2d(const kb_conv_args *args, kb_stream_t stream);
 /* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) followed by the block's first PReLU
  * (models/pointcloud_inpainting.py:70-72); the output may be cropped to Ho x Wo (the reference's F.pad(-1), :154-155). */
 int kb_upsample2x_prelu(const float *x, long x_stride, int N, int H, int W, int C, const float *slope, float *y, long y_stride,
-                        int Ho, int Wo, int round_tf32, const float *mul /* optional [N,Ho,Wo] factor, as kb_conv_out.mul */,
-                        kb_stream_t stream);
+                        int Ho, int Wo, int round_tf32 /* 1: round to TF32; 2: y holds fp16, y_stride counts halves */,
+                        const float *mul /* optional [N,Ho,Wo] factor, as kb_conv_out.mul */, kb_stream_t stream);
 /* Mask bookkeeping of PartialConv2d(multi_channel=True), utils/partial_conv.py:43-69, for masks whose channels are identical
  * (all masks of models/partial_inpainting.py): mask [N,H,W] of {0,1} (NULL = no mask = ones) ->
  * update_mask = clamp(Cin * box_k(mask), 0, 1) and ratio = Cin*k*k / (Cin * box_k(mask) + 1e-8) * update_mask, both [N,Ho,Wo]. */

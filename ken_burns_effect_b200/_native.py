@@ -28,7 +28,7 @@ class KBFrameParams(ctypes.Structure):
 
 
 class KBConvOut(ctypes.Structure):
-    _fields_ = [("ptr", c_void), ("pixel_stride", c_long), ("slope", c_void), ("mul", c_void), ("round_tf32", c_int), ("_pad", c_int)]
+    _fields_ = [("ptr", c_void), ("pixel_stride", c_long), ("slope", c_void), ("mul", c_void), ("round_tf32", c_int), ("store_f16", c_int)]
 
 
 class KBConvArgs(ctypes.Structure):
@@ -36,7 +36,8 @@ class KBConvArgs(ctypes.Structure):
                 ("w_packed", c_void), ("bias", c_void), ("Cout", c_int), ("ksize", c_int), ("stride", c_int),
                 ("pad", c_int), ("res", c_void), ("res_stride", c_long), ("pc_ratio", c_void), ("pc_um", c_void), ("n_out", c_int),
                 ("out", KBConvOut * 3),
-                ("out_H", c_int), ("out_W", c_int), ("tile_w", c_int), ("n_block", c_int), ("stages", c_int), ("algo", c_int)]
+                ("out_H", c_int), ("out_W", c_int), ("tile_w", c_int), ("n_block", c_int), ("stages", c_int), ("algo", c_int),
+                ("x_f16", c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol include/kb200.h declares (tests/test_abi.py checks).
@@ -71,6 +72,8 @@ SIGNATURES = {
     "kb_coverage": (c_int, [c_void, c_long, ctypes.POINTER(KBPose), c_int, c_int, c_int, c_double, c_void, c_void, c_void]),
     "kb_conv_packed_floats": (c_long, [c_int, c_int, c_int]),
     "kb_conv_pack_weights": (c_int, [c_void, c_int, c_int, c_int, c_void, c_void, c_void]),
+    "kb_conv_packed_halves": (c_long, [c_int, c_int, c_int]),
+    "kb_conv_pack_weights_f16": (c_int, [c_void, c_int, c_int, c_int, c_void, c_void, c_void]),
     "kb_conv2d": (c_int, [ctypes.POINTER(KBConvArgs), c_void]),
     "kb_upsample2x_prelu": (c_int, [c_void, c_long, c_int, c_int, c_int, c_int, c_void, c_void, c_long, c_int, c_int,
                                     c_int, c_void, c_void]),

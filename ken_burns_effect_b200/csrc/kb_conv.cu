@@ -26,6 +26,7 @@
 // KB_CONV_DEBUG (bit mask, profiling experiments only -- results are WRONG with any bit set): 1 no epilogue stores,
 // 2 no MMAs, 4 no activation loads, 8 no TMEM reads; this is how DESIGN.md's "what bounds the kernel" numbers were taken.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include <mutex>
@@ -114,6 +115,29 @@ __device__ __forceinline__ void umma_tf32_lh(uint32_t tmem_d, uint32_t a_lo, uin
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f16 (fp16 operands, fp32 accumulate): K = 16 halves = the same 32 bytes per MMA as kind::tf32, twice the MACs.
+__device__ __forceinline__ void umma_f16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Operand kind is a template parameter of the kernels: a run-time choice inside the issue loop cost the TF32 path 10 %
+// (two predicated UTCHMMA per step on the one thread everything waits for).
+template <bool F16>
+__device__ __forceinline__ void umma_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if (F16) umma_f16_lh(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+  else umma_tf32_lh(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+}
 // One lane of a converged warp.
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -173,6 +197,7 @@ struct ConvOut {
   const float *slope;   // per-channel PReLU applied to this output (nullptr = identity)
   const float *mul;     // per-pixel factor applied last (the {0,1} mask a partial-conv consumer multiplies its input with)
   int round_tf32;       // round to TF32 (the value only feeds convolutions)
+  int f16;              // store as fp16 (ptr points at halves, stride counts halves): the input of a kind::f16 convolution
 };
 
 struct ConvKernelParams {
@@ -203,6 +228,8 @@ struct ConvKernelParams {
   int n_blocks;
   long work_items;      // tiles * n_blocks
   int debug;            // KB_CONV_DEBUG bit mask (profiling experiments only, see the file header)
+  int f16;              // operands are fp16 (activations and packed filters): kind::f16, 64 channels per 128-byte chunk
+  int cpc;              // channels per chunk: 32 (tf32) or 64 (f16) -- a chunk is always one 128-byte swizzle row per pixel
 };
 
 
@@ -218,6 +245,18 @@ struct ConvKernelParams {
 // the residual of a chunk is requested BEFORE the accumulator is waited for, and the TMEM load overlaps both.
 // PReLU as torch computes it (x >= 0 ? x : w * x): a compare and a predicated multiply.
 __device__ __forceinline__ float prelu1(float v, float s) { return v < 0.f ? __fmul_rn(v, s) : v; }
+
+// 4 consecutive channels of one output pixel as fp16 (8 bytes), saturated to the fp16 range
+__device__ __forceinline__ void store_half4(float *base_as_float, long half_index, float4 w) {
+  const float lim = 65504.0f;
+  w.x = fminf(fmaxf(w.x, -lim), lim); w.y = fminf(fmaxf(w.y, -lim), lim);
+  w.z = fminf(fmaxf(w.z, -lim), lim); w.w = fminf(fmaxf(w.w, -lim), lim);
+  const __half2 lo = __floats2half2_rn(w.x, w.y), hi = __floats2half2_rn(w.z, w.w);
+  uint2 v;
+  v.x = *reinterpret_cast<const uint32_t *>(&lo);
+  v.y = *reinterpret_cast<const uint32_t *>(&hi);
+  *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(base_as_float) + half_index) = v;
+}
 
 struct EpiSmem {
   const float *bias;              // [cpad]   (zeros when the layer has no bias); the slopes of output o follow at
@@ -317,6 +356,7 @@ __device__ __forceinline__ void epilogue_rows(const ConvKernelParams &p, const E
       for (int o = 0; o < p.n_out; ++o) {
         const ConvOut &out = p.out[o];
         float *dst = out.ptr + px.pix * out.stride + n0 + c0;
+        const long hidx = px.pix * out.stride + n0 + c0;           // the same position counted in halves (out.f16)
         const float *slope = out.slope ? es.bias + (1 + o) * es.cpad + n0 + c0 : nullptr;
         const float m = out.mul ? __ldg(out.mul + px.pix) : 1.f;
         const bool rnd = out.round_tf32 != 0;
@@ -329,6 +369,10 @@ __device__ __forceinline__ void epilogue_rows(const ConvKernelParams &p, const E
             w.x = prelu1(w.x, sl.x); w.y = prelu1(w.y, sl.y); w.z = prelu1(w.z, sl.z); w.w = prelu1(w.w, sl.w);
           }
           if (out.mul) { w.x *= m; w.y *= m; w.z *= m; w.w *= m; }
+          if (out.f16) {
+            if (!(p.debug & 1)) store_half4(out.ptr, hidx + 4 * g, w);
+            continue;
+          }
           if (rnd) { w.x = round_tf32(w.x); w.y = round_tf32(w.y); w.z = round_tf32(w.z); w.w = round_tf32(w.w); }
           if (!(p.debug & 1)) *reinterpret_cast<float4 *>(dst + 4 * g) = w;
         }
@@ -361,7 +405,10 @@ __device__ __forceinline__ EpiPixelU epi_pixel_u(const ConvKernelParams &p, int 
   e.um = p.pc_um ? __ldg(p.pc_um + pix) : 1.f;
 #pragma unroll
   for (int o = 0; o < kMaxOut; ++o) {
-    e.dst[o] = o < p.n_out ? p.out[o].ptr + pix * p.out[o].stride : nullptr;
+    e.dst[o] = nullptr;
+    if (o < p.n_out)
+      e.dst[o] = p.out[o].f16 ? reinterpret_cast<float *>(reinterpret_cast<__half *>(p.out[o].ptr) + pix * p.out[o].stride)
+                              : p.out[o].ptr + pix * p.out[o].stride;
     e.mul[o] = (o < p.n_out && p.out[o].mul) ? __ldg(p.out[o].mul + pix) : 1.f;
   }
   return e;
@@ -421,6 +468,10 @@ __device__ __forceinline__ void epilogue_rows_u(const ConvKernelParams &p, const
           if (p.out[o].mul) {
             w.x *= px.mul[o]; w.y *= px.mul[o]; w.z *= px.mul[o]; w.w *= px.mul[o];
           }
+          if (p.out[o].f16) {
+            if (!(p.debug & 1)) store_half4(px.dst[o], c, w);
+            continue;
+          }
           if (p.out[o].round_tf32) {
             w.x = round_tf32(w.x); w.y = round_tf32(w.y); w.z = round_tf32(w.z); w.w = round_tf32(w.w);
           }
@@ -437,6 +488,7 @@ __device__ __forceinline__ void epilogue_rows_u(const ConvKernelParams &p, const
 
 
 // two CTAs per SM: the per-tap kernel is not persistent, one CTA's epilogue overlaps the other's main loop
+template <bool F16>
 __global__ void __launch_bounds__(kConvThreads, 2) k_conv_tf32(const __grid_constant__ CUtensorMap map_a,
                                                             const __grid_constant__ CUtensorMap map_b,
                                                             const ConvKernelParams p) {
@@ -497,7 +549,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) k_conv_tf32(const __grid_cons
           uint8_t *a_dst = smem + (size_t)s * stage_bytes;
           if (leader) {
             mbar_expect_tx(full + s, (uint32_t)stage_bytes);
-            tma_load_4d(&map_a, full + s, a_dst, ck * kChunk, cx + q, cy + r, img);
+            tma_load_4d(&map_a, full + s, a_dst, ck * p.cpc, cx + q, cy + r, img);
             tma_load_3d(&map_b, full + s, a_dst + kABytes, 0, n0, j);
           }
           if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
@@ -505,7 +557,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) k_conv_tf32(const __grid_cons
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const bool leader = elect_one();
-    const uint32_t idesc = (1u << 4) /* D fp32 */ | (2u << 7) /* A tf32 */ | (2u << 10) /* B tf32 */ |
+    const uint32_t fmt = F16 ? 0u : 2u;        // operand format field: 0 = f16, 2 = tf32
+    const uint32_t idesc = (1u << 4) /* D fp32 */ | (fmt << 7) /* A */ | (fmt << 10) /* B */ |
                            ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     const uint64_t tmpl = umma_desc_sw128(0);
     const uint32_t d_hi = (uint32_t)(tmpl >> 32), d_tl = (uint32_t)tmpl;
@@ -521,8 +574,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) k_conv_tf32(const __grid_cons
 #pragma unroll
         for (int k = 0; k < kChunk / 8; ++k)   // UMMA K = 8 tf32 = 32 bytes: advance the start address inside the swizzle row
           if (k < ksteps)
-            umma_tf32_lh(tmem_base, d_tl | ((lo + 2 * k) & 0x3FFF), d_hi, d_tl | ((lo + (kABytes >> 4) + 2 * k) & 0x3FFF), d_hi, idesc,
-                         (uint32_t)((j | k) != 0));
+            umma_lh<F16>(tmem_base, d_tl | ((lo + 2 * k) & 0x3FFF), d_hi, d_tl | ((lo + (kABytes >> 4) + 2 * k) & 0x3FFF), d_hi, idesc,
+                    (uint32_t)((j | k) != 0));
         umma_commit(empty + s);                // slot reusable once these MMAs have read it
       }
       lo += stage_lo;
@@ -599,7 +652,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <int KS>
+template <int KS, bool F16>
 __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid_constant__ CUtensorMap map_a,
                                                                     const __grid_constant__ CUtensorMap map_b,
                                                                     const ConvKernelParams p) {
@@ -644,7 +697,27 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
     uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
     bool first = true;
     TileIter it;
-    for (it.init(p); it.left > 0; it.next(p)) {
+    it.init(p);
+    if (p.resident && it.left > 0) {
+      // Resident filters: ALL panels first, in slot order (chunk-major).  Interleaved with the activation chunks (as the streamed
+      // path does) the producer would wait for a free activation stage while the MMA warp waits for the last panels whenever a
+      // tile has more chunks than there are activation stages -- e.g. 144 fp16 channels = 3 chunks with 2 stages left next to
+      // 27 resident panels.
+      const int cn = it.nb * p.Npad;
+      for (int ck = 0; ck < p.chunks; ++ck) {
+        int j = ck;
+        for (int tap = 0; tap < kTaps; ++tap, j += p.chunks) {
+          mbar_wait(b_empty + sb, phb ^ 1u);
+          if (leader) {
+            mbar_expect_tx(b_full + sb, (uint32_t)b_bytes);
+            tma_load_3d(&map_b, b_full + sb, smem_b + (size_t)sb * b_bytes, 0, cn, j);
+          }
+          if (++sb == (uint32_t)p.b_stages) { sb = 0; phb ^= 1u; }
+        }
+      }
+      first = false;
+    }
+    for (; it.left > 0; it.next(p)) {
       const int img = it.img;
       const int cx = it.tx * kHaloTileW - p.pad, cy = it.ty * kHaloTileH - p.pad, cn = it.nb * p.Npad;
       for (int ck = 0; ck < p.chunks; ++ck) {
@@ -654,7 +727,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(a_full + sa)) : "memory");
           } else {
             mbar_expect_tx(a_full + sa, (uint32_t)kBoxBytes);
-            tma_load_4d(&map_a, a_full + sa, smem_a + (size_t)sa * kAStage, ck * kChunk, cx, cy, img);
+            tma_load_4d(&map_a, a_full + sa, smem_a + (size_t)sa * kAStage, ck * p.cpc, cx, cy, img);
           }
         }
         if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; }
@@ -679,7 +752,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
     // registers one MMA at a time: ncu showed ~17 dependent instructions (~128 cycles) per MMA on the issuing thread, i.e.
     // the tensor pipe (16-64 cycles per MMA) waited for its own issue loop and every other role waited for the tensor pipe.
     const bool leader = elect_one();
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    const uint32_t fmt = F16 ? 0u : 2u;        // operand format field: 0 = f16, 2 = tf32
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     const uint64_t tmpl_a = umma_desc_sw128_sbo(0, kPitch * kChunk * 4), tmpl_b = umma_desc_sw128(0);
     const uint32_t a_hi = (uint32_t)(tmpl_a >> 32), b_hi = (uint32_t)(tmpl_b >> 32);
     const uint32_t a_tl = (uint32_t)tmpl_a, b_tl = (uint32_t)tmpl_b;          // low words without the address field
@@ -712,7 +786,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
 #pragma unroll
               for (int k = 0; k < kChunk / 8; ++k)
                 if (k < ksteps)
-                  umma_tf32_lh(d_tmem, A0 + a_off + 2 * k, a_hi, B0 + 2 * k, b_hi, idesc, (uint32_t)((ck != 0) | (tap != 0) | (k != 0)));
+                  umma_lh<F16>(d_tmem, A0 + a_off + 2 * k, a_hi, B0 + 2 * k, b_hi, idesc, (uint32_t)((ck != 0) | (tap != 0) | (k != 0)));
               B0 += b_step_lo;
             }
           } else {
@@ -744,7 +818,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
               if (!(p.debug & 2)) {
 #pragma unroll
                 for (int k = 0; k < kChunk / 8; ++k)   // (streamed filters = wide layers: no padding steps worth skipping)
-                    umma_tf32_lh(d_tmem, A0 + a_off + 2 * k, a_hi, B0 + 2 * k, b_hi, idesc, (uint32_t)((ck != 0) | (tap != 0) | (k != 0)));
+                    umma_lh<F16>(d_tmem, A0 + a_off + 2 * k, a_hi, B0 + 2 * k, b_hi, idesc, (uint32_t)((ck != 0) | (tap != 0) | (k != 0)));
               }
               umma_commit(b_empty + sb);
             }
@@ -808,6 +882,28 @@ __global__ void __launch_bounds__(256) k_pack_weights(const float *__restrict__ 
   dst[i] = round_tf32(v);
 }
 
+// The same filters for kind::f16: [tap][chunk of 64 channels][Cout_pad16][64] halves (one 128-byte row per output channel and chunk).
+__global__ void __launch_bounds__(256) k_pack_weights_f16(const float *__restrict__ w, int Cout, int Cin, int ksize, int chunks,
+                                                          int Cout_pad, const float *__restrict__ out_scale, __half *__restrict__ dst,
+                                                          long total) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cpc = 2 * kChunk;
+  const int ci = (int)(i % cpc);
+  long r = i / cpc;
+  const int o = (int)(r % Cout_pad);
+  r /= Cout_pad;
+  const int ck = (int)(r % chunks);
+  const int tap = (int)(r / chunks);
+  const int c = ck * cpc + ci;
+  float v = 0.f;
+  if (o < Cout && c < Cin) {
+    v = w[((long)o * Cin + c) * ksize * ksize + tap];
+    if (out_scale) v *= out_scale[o];
+  }
+  dst[i] = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
+}
+
 // ---- elementwise companions of the conv stacks (NHWC) ---------------------------------------------------------
 // bilinear x2 (align_corners=False) followed by the per-channel PReLU of the Upsample block
 // (models/pointcloud_inpainting.py:70-72); output optionally cropped to (Ho, Wo) <= (2H, 2W).
@@ -844,9 +940,10 @@ __global__ void __launch_bounds__(256) k_upsample2x_prelu(const float *__restric
     if (slope && c < C) v = v > 0.f ? v : v * __ldg(slope + c);
     if (c >= C) v = 0.f;
     if (mul) v *= __ldg(mul + ((long)n * Ho + oy) * Wo + ox);
-    o[e] = round ? round_tf32(v) : v;
+    o[e] = round == 1 ? round_tf32(v) : v;
   }
-  *reinterpret_cast<float4 *>(y + (((long)n * Ho + oy) * Wo + ox) * ys + 4 * cg) = make_float4(o[0], o[1], o[2], o[3]);
+  if (round == 2) store_half4(y, (((long)n * Ho + oy) * Wo + ox) * ys + 4 * cg, make_float4(o[0], o[1], o[2], o[3]));   // fp16 output
+  else *reinterpret_cast<float4 *>(y + (((long)n * Ho + oy) * Wo + ox) * ys + 4 * cg) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // y = prelu(x) (slope per channel; nullptr = copy), NHWC with independent pixel strides.
@@ -863,9 +960,10 @@ __global__ void __launch_bounds__(256) k_prelu_nhwc(const float *__restrict__ x,
     const int c = 4 * cg + e;
     if (slope && c < C) a[e] = a[e] > 0.f ? a[e] : a[e] * __ldg(slope + c);
     if (c >= C) a[e] = 0.f;
-    if (round) a[e] = round_tf32(a[e]);
+    if (round == 1) a[e] = round_tf32(a[e]);
   }
-  *reinterpret_cast<float4 *>(y + pix * ys + 4 * cg) = make_float4(a[0], a[1], a[2], a[3]);
+  if (round == 2) store_half4(y, pix * ys + 4 * cg, make_float4(a[0], a[1], a[2], a[3]));                                 // fp16 output
+  else *reinterpret_cast<float4 *>(y + pix * ys + 4 * cg) = make_float4(a[0], a[1], a[2], a[3]);
 }
 
 // 2x2 max-pool, stride 2, ceil_mode=True (models/disparity_estimation.py:90), NHWC.
@@ -1005,17 +1103,35 @@ int kb_conv_pack_weights(const float *w_oihw, int Cout, int Cin, int ksize, cons
 
 
 
+long kb_conv_packed_halves(int Cout, int Cin, int ksize) {
+  if (Cout <= 0 || Cin <= 0 || ksize <= 0) return 0;
+  const long cpc = 2 * kChunk, chunks = (Cin + cpc - 1) / cpc, cout_pad = (Cout + 15) / 16 * 16;
+  return (long)ksize * ksize * chunks * cout_pad * cpc;
+}
+
+int kb_conv_pack_weights_f16(const float *w_oihw, int Cout, int Cin, int ksize, const float *out_scale, void *packed,
+                             kb_stream_t stream) {
+  KB_REQUIRE(w_oihw && packed && Cout > 0 && Cin > 0 && ksize > 0, "kb_conv_pack_weights_f16: bad arguments");
+  const int cpc = 2 * kChunk, chunks = (Cin + cpc - 1) / cpc, cout_pad = (Cout + 15) / 16 * 16;
+  const long total = kb_conv_packed_halves(Cout, Cin, ksize);
+  k_pack_weights_f16<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, ksize, chunks, cout_pad, out_scale,
+                                                                        reinterpret_cast<__half *>(packed), total);
+  count_launch();
+  return check_launch("kb_conv_pack_weights_f16");
+}
+
 static int env_int(const char *name, int dflt) {
   const char *v = getenv(name);
   return v ? atoi(v) : dflt;
 }
 
-static int make_weight_map(EncodeTiledFn enc, const float *w_packed, int cout_pad, int J, int npad, CUtensorMap *map) {
-  cuuint64_t dims[3] = {(cuuint64_t)kChunk, (cuuint64_t)cout_pad, (cuuint64_t)J};
+static int make_weight_map(EncodeTiledFn enc, const float *w_packed, int cout_pad, int J, int npad, int f16, CUtensorMap *map) {
+  const int cpc = f16 ? 2 * kChunk : kChunk;      // elements per 128-byte row
+  cuuint64_t dims[3] = {(cuuint64_t)cpc, (cuuint64_t)cout_pad, (cuuint64_t)J};
   cuuint64_t strides[2] = {(cuuint64_t)kChunk * 4, (cuuint64_t)kChunk * 4 * cout_pad};
-  cuuint32_t box[3] = {(cuuint32_t)kChunk, (cuuint32_t)npad, 1};
+  cuuint32_t box[3] = {(cuuint32_t)cpc, (cuuint32_t)npad, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(w_packed), dims, strides, box, estr,
+  CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(w_packed), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1027,13 +1143,14 @@ static int make_weight_map(EncodeTiledFn enc, const float *w_packed, int cout_pa
 
 // NHWC activations as a 4-D tensor {C, W, H, N}; box {32, box_w, box_h, 1} traversed with the convolution stride.
 static int make_act_map(EncodeTiledFn enc, const kb_conv_args *a, int box_w, int box_h, int stride, CUtensorMap *map) {
+  const int esz = a->x_f16 ? 2 : 4, cpc = a->x_f16 ? 2 * kChunk : kChunk;
   cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->N};
-  cuuint64_t strides[3] = {(cuuint64_t)a->x_stride * 4, (cuuint64_t)a->x_stride * 4 * a->W,
-                           (cuuint64_t)a->x_stride * 4 * a->W * a->H};
-  cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint64_t strides[3] = {(cuuint64_t)a->x_stride * esz, (cuuint64_t)a->x_stride * esz * a->W,
+                           (cuuint64_t)a->x_stride * esz * a->W * a->H};
+  cuuint32_t box[4] = {(cuuint32_t)cpc, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   // (L2 promotion NONE / 64B / 128B / 256B measure the same here)
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(a->x), dims, strides, box, estr,
+  CUresult r = enc(map, a->x_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(a->x), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1055,9 +1172,13 @@ static int raise_smem_limit() {
   static bool done_dev[kMaxDevices] = {};
   bool &done = done_dev[current_device()];
   if (done) return 0;
-  cudaError_t e = cudaFuncSetAttribute(k_conv_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  const int big = 227 * 1024;
+  cudaError_t e = cudaFuncSetAttribute(k_conv_tf32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_tf32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   if (e != cudaSuccess) {
     set_error("kb_conv2d: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     return (int)e;
@@ -1079,7 +1200,8 @@ static int sm_count() {
 int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
   KB_REQUIRE(a && a->x && a->w_packed, "kb_conv2d: null argument");
   KB_REQUIRE(a->N > 0 && a->H > 0 && a->W > 0 && a->Cin > 0 && a->Cout > 0, "kb_conv2d: bad shape");
-  KB_REQUIRE(a->x_stride >= a->Cin && a->x_stride % 4 == 0, "kb_conv2d: x_stride must be a multiple of 4 floats and >= Cin");
+  KB_REQUIRE(a->x_stride >= a->Cin && a->x_stride % (a->x_f16 ? 8 : 4) == 0,
+             "kb_conv2d: x_stride must be a multiple of 16 bytes and >= Cin");
   KB_REQUIRE((reinterpret_cast<uintptr_t>(a->x) & 15) == 0, "kb_conv2d: x must be 16-byte aligned");
   KB_REQUIRE(a->ksize >= 1 && a->ksize <= 7 && (a->stride == 1 || a->stride == 2) && a->pad >= 0, "kb_conv2d: unsupported filter");
   KB_REQUIRE(a->n_out >= 1 && a->n_out <= kMaxOut, "kb_conv2d: need 1..3 outputs");
@@ -1107,8 +1229,11 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
   if (algo == 0) algo = halo_ok ? 2 : 1;
   KB_REQUIRE(algo == 1 || (algo == 2 && halo_ok), "kb_conv2d: algo 2 needs stride 1, ksize <= 3, 'same' padding");
 
-  p.chunks = (a->Cin + kChunk - 1) / kChunk;
-  p.last_ksteps = ((a->Cin - (p.chunks - 1) * kChunk) + 7) / 8;
+  p.f16 = a->x_f16 ? 1 : 0;
+  p.cpc = p.f16 ? 2 * kChunk : kChunk;                 // channels per 128-byte chunk
+  const int kstep_ch = p.cpc / 4;                      // channels per MMA K step (32 bytes): 8 tf32 or 16 f16
+  p.chunks = (a->Cin + p.cpc - 1) / p.cpc;
+  p.last_ksteps = ((a->Cin - (p.chunks - 1) * p.cpc) + kstep_ch - 1) / kstep_ch;
   p.ksize = a->ksize;
   p.stride = a->stride;
   p.pad = a->pad;
@@ -1145,7 +1270,7 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
   p.vec = (a->Cout % 4 == 0) && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0;
   for (int o = 0; o < a->n_out; ++o) {
     if (reinterpret_cast<uintptr_t>(a->out[o].slope) & 15) p.vec = 0;
-    KB_REQUIRE(a->out[o].ptr && a->out[o].pixel_stride % 4 == 0 && a->out[o].pixel_stride >= p.Cout4 &&
+    KB_REQUIRE(a->out[o].ptr && a->out[o].pixel_stride % (a->out[o].store_f16 ? 8 : 4) == 0 && a->out[o].pixel_stride >= p.Cout4 &&
                    (reinterpret_cast<uintptr_t>(a->out[o].ptr) & 15) == 0,
                "kb_conv2d: output %d: pointer / stride must be 16-byte aligned and hold %d channels", o, p.Cout4);
     p.out[o].ptr = a->out[o].ptr;
@@ -1153,6 +1278,7 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
     p.out[o].slope = a->out[o].slope;
     p.out[o].mul = a->out[o].mul;
     p.out[o].round_tf32 = a->out[o].round_tf32;
+    p.out[o].f16 = a->out[o].store_f16;
   }
   KB_REQUIRE((a->pc_ratio == nullptr) == (a->pc_um == nullptr), "kb_conv2d: pc_ratio and pc_um come together");
   p.pc_ratio = a->pc_ratio;
@@ -1160,7 +1286,7 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
   int rc = raise_smem_limit();
   if (rc) return rc;
   CUtensorMap map_a, map_b;
-  rc = make_weight_map(enc, a->w_packed, cout_pad, J, npad, &map_b);
+  rc = make_weight_map(enc, a->w_packed, cout_pad, J, npad, p.f16, &map_b);
   if (rc) return rc;
   const int b_bytes = npad * kChunk * 4;
   const size_t smem_cap = 227 * 1024;
@@ -1178,7 +1304,8 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
     const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 32 + epi_bytes;
     KB_REQUIRE(smem <= smem_cap, "kb_conv2d: pipeline does not fit shared memory");
     dim3 grid((unsigned)tiles, (unsigned)n_blocks);
-    k_conv_tf32<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+    if (p.f16) k_conv_tf32<true><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+    else k_conv_tf32<false><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
     count_launch();
     return check_launch("kb_conv2d");
   }
@@ -1214,8 +1341,13 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
   const size_t smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * b_bytes + bar_bytes + epi_bytes;
   KB_REQUIRE(smem <= smem_cap, "kb_conv2d: pipeline does not fit shared memory");
   const unsigned grid = (unsigned)min((long)sm_count(), p.work_items);
-  if (a->ksize == 1) k_conv_halo_tf32<1><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
-  else k_conv_halo_tf32<3><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  if (a->ksize == 1) {
+    if (p.f16) k_conv_halo_tf32<1, true><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+    else k_conv_halo_tf32<1, false><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  } else {
+    if (p.f16) k_conv_halo_tf32<3, true><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+    else k_conv_halo_tf32<3, false><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  }
   count_launch();
   return check_launch("kb_conv2d");
 }
@@ -1224,8 +1356,9 @@ int kb_upsample2x_prelu(const float *x, long x_stride, int N, int H, int W, int 
                         int Ho, int Wo, int round_tf32, const float *mul, kb_stream_t stream) {
   KB_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0 && Ho <= 2 * H && Wo <= 2 * W,
              "kb_upsample2x_prelu: bad arguments");
-  KB_REQUIRE(x_stride % 4 == 0 && y_stride % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0,
-             "kb_upsample2x_prelu: pointers must be 16-byte aligned, strides multiples of 4 floats");
+  KB_REQUIRE(x_stride % 4 == 0 && y_stride % (round_tf32 == 2 ? 8 : 4) == 0 &&
+                 ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0,
+             "kb_upsample2x_prelu: pointers must be 16-byte aligned, strides multiples of 16 bytes");
   const int C4 = (C + 3) / 4;
   const long total = (long)N * Ho * Wo * C4;
   k_upsample2x_prelu<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, x_stride, H, W, C4, slope, C, y, y_stride, Ho, Wo,
@@ -1236,9 +1369,9 @@ int kb_upsample2x_prelu(const float *x, long x_stride, int N, int H, int W, int 
 
 int kb_prelu_nhwc(const float *x, long x_stride, long pixels, int C, const float *slope, float *y, long y_stride, int round_tf32,
                   kb_stream_t stream) {
-  KB_REQUIRE(x && y && pixels > 0 && C > 0 && x_stride % 4 == 0 && y_stride % 4 == 0 &&
+  KB_REQUIRE(x && y && pixels > 0 && C > 0 && x_stride % 4 == 0 && y_stride % (round_tf32 == 2 ? 8 : 4) == 0 &&
                  ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0,
-             "kb_prelu_nhwc: bad arguments (16-byte aligned pointers, strides multiples of 4 floats)");
+             "kb_prelu_nhwc: bad arguments (16-byte aligned pointers, strides multiples of 16 bytes)");
   const int C4 = (C + 3) / 4;
   const long total = pixels * C4;
   k_prelu_nhwc<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, x_stride, slope, C, C4, y, y_stride, round_tf32, total);

@@ -96,9 +96,10 @@ class Disparity(nn.Module):
     def _forward_b200(self, tensorImage, tensorSemantics):
         x = cs.to_nhwc(tensorImage)
         sem, = cs.conv2d(cs.to_nhwc(tensorSemantics), cs.packed(self.moduleSemantics), [(None, False, None)])
-        row0 = cs.grid_forward_nhwc(self, self.FEATURES, lambda outs: cs.conv2d(x, cs.packed(self.moduleImage), outs),
-                                    semantics_res=sem)
-        return cs.to_nchw(cs.head_nhwc(self.moduleDisparity, row0))
+        with cs.f16_operands():       # every `round` output of the GridNet is read by convolutions only
+            row0 = cs.grid_forward_nhwc(self, self.FEATURES, lambda outs: cs.conv2d(x, cs.packed(self.moduleImage), outs),
+                                        semantics_res=sem)
+            return cs.to_nchw(cs.head_nhwc(self.moduleDisparity, row0))
 
     def forward(self, tensorImage, tensorSemantics):
         if tensorImage.is_cuda:

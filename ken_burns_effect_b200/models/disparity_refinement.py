@@ -41,6 +41,10 @@ class Refine(nn.Module):
     def _forward_b200(self, img, disp):
         """The same network on libkb200 convolutions.  torch.cat of the reference (:100-104) = channel slices of three
         NHWC concat buffers that the producing convolutions write directly."""
+        with cs.f16_operands():       # every `round` output / up-sampled tensor of this stack is read by convolutions only
+            return self._forward_b200_body(img, disp)
+
+    def _forward_b200_body(self, img, disp):
         N, _, H, W = img.shape
         dev = img.device
         h2, w2, h4, w4 = (H + 1) // 2, (W + 1) // 2, ((H + 1) // 2 + 1) // 2, ((W + 1) // 2 + 1) // 2

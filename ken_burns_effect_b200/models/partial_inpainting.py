@@ -180,6 +180,10 @@ class Inpaint(_DenseInpaint):
         return cs.conv2d(t, cs.packed(c2), make_outs(k), res=res, crop=crop, partial=(r2, u2)), k
 
     def _forward_b200(self, tensorData, tensorMasks):
+        with cs.f16_operands():       # every `round` output / up-sampled tensor of this stack is read by convolutions only
+            return self._forward_b200_body(tensorData, tensorMasks)
+
+    def _forward_b200_body(self, tensorData, tensorMasks):
         m = self._modules
         F_ = self.FEATURES
         R = len(F_)

@@ -81,8 +81,9 @@ class Inpaint(nn.Module):
     def _grid_rows_b200(self, buf):
         """The GridNet + heads on an NHWC input buffer [N,H,W,72] whose channels 0..68 are cat([data, mask])."""
         x = buf[..., :69]
-        row0 = cs.grid_forward_nhwc(self, self.FEATURES, lambda outs: cs.run_block(self.moduleInput, x, outs, x_raw=x))
-        return cs.to_nchw(cs.head_nhwc(self.moduleImage, row0)), cs.to_nchw(cs.head_nhwc(self.moduleDisparity, row0))
+        with cs.f16_operands():       # every `round` output of this stack is read by convolutions only
+            row0 = cs.grid_forward_nhwc(self, self.FEATURES, lambda outs: cs.run_block(self.moduleInput, x, outs, x_raw=x))
+            return cs.to_nchw(cs.head_nhwc(self.moduleImage, row0)), cs.to_nchw(cs.head_nhwc(self.moduleDisparity, row0))
 
     def _render_rows_b200(self, img, disp, points_shifted, objectCommon, dblFocal):
         """Context features -> 68-channel splat -> mask -> normalised, masked network input, all in NHWC: the context
@@ -97,8 +98,9 @@ class Inpaint(nn.Module):
         rows = torch.empty(1, H, W, 68, device=img.device, dtype=torch.float32)
         cs.to_nhwc(torch.cat([img, disp], 1), dst=rows[..., 0:4])
         c0, a0, c1, a1 = list(self.moduleContext)
-        t, = cs.conv2d(rows[..., 0:4], cs.packed(c0), [(a0.weight, True, None)])
-        cs.conv2d(t, cs.packed(c1), [(a1.weight, False, rows[..., 4:68])])
+        with cs.f16_operands():       # the intermediate of the two context convolutions is read by the second one only
+            t, = cs.conv2d(rows[..., 0:4], cs.packed(c0), [(a0.weight, True, None)])
+            cs.conv2d(t, cs.packed(c1), [(a1.weight, False, rows[..., 4:68])])
         return rows
 
     def _splat_rows_b200(self, rows, points_shifted, objectCommon, dblFocal):

@@ -33,15 +33,42 @@ def round4(c):
     return (c + 3) & ~3
 
 
-def new_act(N, H, W, C, device):
-    """Fresh NHWC activation with C logical channels (allocation padded to a multiple of 4 channels)."""
-    return torch.empty(N, H, W, round4(C), device=device, dtype=torch.float32)[..., :C]
+# Operand precision of the convolutions.  False: TF32 operands read from fp32 activations (the reference's own arithmetic under
+# PyTorch's default cudnn.allow_tf32).  True: every tensor that is ONLY ever the input of a convolution -- the PReLU'd, already
+# TF32-rounded copies the epilogues write (`round` outputs) and the up-sampled tensors -- is stored as fp16 (the same 10 mantissa
+# bits, half the bytes) and those convolutions run tcgen05 kind::f16: twice the MACs per MMA at the same operand-fetch cost
+# (DESIGN.md section 5).  Sums, residual streams, biases and network outputs stay fp32.  fp16's RANGE (|x| <= 65504, saturated)
+# is the one thing TF32 does not share: KB200_CONV_F16=0 selects the TF32 path.
+import contextlib as _contextlib
+import os as _os0
+F16_ENABLED = _os0.environ.get("KB200_CONV_F16", "0") == "1"
+F16 = False          # what conv2d / upsample2x_prelu read; raised inside f16_operands() by the stacks that are fp16-clean
+
+
+@_contextlib.contextmanager
+def f16_operands():
+    """Inside this scope `round` outputs are fp16 and their consumers run kind::f16 -- entered by the network forwards whose
+    `round` outputs are read by convolutions only (the GridNets); a no-op unless KB200_CONV_F16=1."""
+    global F16
+    old = F16
+    F16 = F16_ENABLED
+    try:
+        yield
+    finally:
+        F16 = old
+
+
+def new_act(N, H, W, C, device, dtype=torch.float32):
+    """Fresh NHWC activation with C logical channels (allocation padded so that a pixel is a multiple of 16 bytes)."""
+    pad = 8 if dtype == torch.float16 else 4
+    return torch.empty(N, H, W, (C + pad - 1) // pad * pad, device=device, dtype=dtype)[..., :C]
 
 
 def _check_act(t):
-    if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.stride(3) == 1 and t.stride(2) % 4 == 0
+    unit = 8 if t.dtype == torch.float16 else 4
+    if not (t.is_cuda and t.dtype in (torch.float32, torch.float16) and t.dim() == 4 and t.stride(3) == 1 and t.stride(2) % unit == 0
             and t.stride(1) == t.stride(2) * t.size(2) and t.stride(0) == t.stride(1) * t.size(1)):
-        raise RuntimeError(f"not an NHWC activation view: shape {tuple(t.shape)} strides {t.stride()}")
+        raise RuntimeError(f"not an NHWC activation view: shape {tuple(t.shape)} strides {t.stride()} dtype {t.dtype}")
     return t
 
 
@@ -65,6 +92,19 @@ class PackedConv:
         self.w = torch.empty(n, device=w.device, dtype=torch.float32)
         nat.check(L.kb_conv_pack_weights(_ptr(w.contiguous()), self.Cout, self.Cin, self.k, _ptr(scale), _ptr(self.w),
                                          _stream()), "kb_conv_pack_weights")
+        self._w16 = None
+        self._src = (w, scale)
+
+    @property
+    def w16(self):
+        """The same filters as fp16 panels (kind::f16), packed on first use."""
+        if self._w16 is None:
+            L = nat.lib()
+            w, scale = self._src
+            self._w16 = torch.empty(L.kb_conv_packed_halves(self.Cout, self.Cin, self.k), device=w.device, dtype=torch.float16)
+            nat.check(L.kb_conv_pack_weights_f16(_ptr(w.contiguous()), self.Cout, self.Cin, self.k, _ptr(scale), _ptr(self._w16),
+                                                 _stream()), "kb_conv_pack_weights_f16")
+        return self._w16
 
 
 def packed(conv, bn=None):
@@ -93,7 +133,8 @@ def conv2d(x, pc, outs, res=None, crop=None, tile_w=0, n_block=0, stages=0, algo
         Ho, Wo = min(Ho, crop[0]), min(Wo, crop[1])
     a = nat.KBConvArgs()
     a.x, a.N, a.H, a.W, a.Cin, a.x_stride = x.data_ptr(), N, H, W, Cin, x.stride(2)
-    a.w_packed, a.bias = pc.w.data_ptr(), pc.bias.data_ptr()
+    a.x_f16 = 1 if x.dtype == torch.float16 else 0
+    a.w_packed, a.bias = (pc.w16 if a.x_f16 else pc.w).data_ptr(), pc.bias.data_ptr()
     a.Cout, a.ksize, a.stride, a.pad = pc.Cout, pc.k, pc.stride, pc.pad
     if res is not None:
         _check_act(res)
@@ -118,8 +159,8 @@ def conv2d(x, pc, outs, res=None, crop=None, tile_w=0, n_block=0, stages=0, algo
                 raise RuntimeError(f"conv2d: mul mask must be contiguous fp32 {(N, Ho, Wo)}, got {tuple(mul.shape)}")
             a.out[i].mul = mul.data_ptr()
             keep.append(mul)
-        if dst is None:
-            dst = new_act(N, Ho, Wo, pc.Cout, x.device)
+        if dst is None:     # a `round` output only ever feeds convolutions: fp16 when the fp16 operand path is on
+            dst = new_act(N, Ho, Wo, pc.Cout, x.device, torch.float16 if (rnd and F16) else torch.float32)
         _check_act(dst)
         if tuple(dst.shape) != (N, Ho, Wo, pc.Cout):
             raise RuntimeError(f"conv2d: destination {tuple(dst.shape)} does not match output {(N, Ho, Wo, pc.Cout)}")
@@ -129,6 +170,7 @@ def conv2d(x, pc, outs, res=None, crop=None, tile_w=0, n_block=0, stages=0, algo
             keep.append(s)
             a.out[i].slope = s.data_ptr()
         a.out[i].round_tf32 = 1 if rnd else 0
+        a.out[i].store_f16 = 1 if dst.dtype == torch.float16 else 0
         result.append(dst)
     a.out_H, a.out_W = (Ho, Wo) if crop is not None else (0, 0)
     a.tile_w, a.n_block, a.stages, a.algo = tile_w, n_block, stages, algo
@@ -141,11 +183,15 @@ def upsample2x_prelu(x, slope, out_hw=None, rnd=True, mul=None):
     _check_act(x)
     N, H, W, C = x.shape
     Ho, Wo = (2 * H, 2 * W) if out_hw is None else out_hw
-    y = new_act(N, Ho, Wo, C, x.device)
+    if x.dtype != torch.float32:
+        raise RuntimeError("upsample2x_prelu reads the raw fp32 value of the coarser row")
+    f16 = bool(rnd and F16)
+    y = new_act(N, Ho, Wo, C, x.device, torch.float16 if f16 else torch.float32)
     if mul is not None and not (mul.is_cuda and mul.dtype == torch.float32 and mul.is_contiguous() and tuple(mul.shape) == (N, Ho, Wo)):
         raise RuntimeError(f"upsample2x_prelu: mul mask must be contiguous fp32 {(N, Ho, Wo)}")
     nat.check(nat.lib().kb_upsample2x_prelu(_ptr(x), x.stride(2), N, H, W, C, _ptr(slope.detach()) if slope is not None else None,
-                                            _ptr(y), y.stride(2), Ho, Wo, 1 if rnd else 0, _ptr(mul), _stream()), "kb_upsample2x_prelu")
+                                            _ptr(y), y.stride(2), Ho, Wo, 2 if f16 else (1 if rnd else 0), _ptr(mul), _stream()),
+              "kb_upsample2x_prelu")
     return y
 
 
@@ -255,6 +301,8 @@ def grid_forward_nhwc(module, features, stem, semantics_res=None):
         need_raw = c < 3 or r > 0 or (r == 0 and c == 3)
         if need_raw:
             keys.append('raw'); out.append((None, False, None))
+        if r == 0 and c == 3 and F16:
+            keys.append('head'); out.append((None, True, None))      # what the heads' first convolutions read (no PReLU before them)
         if c < 3:
             keys.append('basic'); out.append((pre_slope(m[grid_name(r, c, r, c + 1)]), True, None))
         if c in (0, 1) and r < R - 1:
@@ -289,7 +337,7 @@ def grid_forward_nhwc(module, features, stem, semantics_res=None):
                 t1, = run_block(basic, V[r]['basic'], [(None, False, None)], x_raw=V[r]['raw'])
                 hw = (t1.size(1), t1.size(2))
                 V[r] = cell(keys, run_block(m[grid_name(r + 1, c, r, c)], V[r + 1]['raw'], out, extra_res=t1, crop=hw))
-    return V[0]['raw']
+    return V[0]['raw'] if 'head' not in V[0] else (V[0]['raw'], V[0]['head'])
 
 
 # -----------------------------------------------------------------------------------------------------------------
@@ -352,5 +400,7 @@ def graphed(owner, tag, fn, *tensors):
 
 
 def head_nhwc(block, x_raw):
-    """Basic('conv-relu-conv') head with its 1x1 shortcut (moduleImage / moduleDisparity)."""
-    return run_block(block, x_raw, [(None, False, None)], x_raw=x_raw)[0]
+    """Basic('conv-relu-conv') head with its 1x1 shortcut (moduleImage / moduleDisparity).  x_raw: the raw row-0 value, or
+    (raw fp32, fp16 copy) from grid_forward_nhwc under f16_operands()."""
+    x_in, x_raw = (x_raw[1], x_raw[0]) if isinstance(x_raw, tuple) else (x_raw, x_raw)
+    return run_block(block, x_in, [(None, False, None)], x_raw=x_raw)[0]

@@ -197,3 +197,36 @@ def test_networks_vs_reference_goldens():
         json.dump(vals, f, indent=1)
     for k, v in vals.items():
         assert v < NETWORK_BAR, (k, v, vals)
+
+
+F16_CASES = [
+    (32, 32, 3, 1, 1, 64, 96), (32, 32, 3, 1, 1, 37, 53), (64, 64, 3, 1, 1, 40, 52), (69, 32, 3, 1, 1, 33, 47),
+    (128, 64, 3, 1, 1, 30, 44), (256, 256, 3, 1, 1, 24, 32), (64, 128, 3, 2, 1, 48, 64), (32, 64, 3, 2, 1, 45, 61),
+    (96, 32, 1, 1, 0, 33, 47), (32, 3, 3, 1, 1, 40, 40),
+]
+
+
+@pytest.mark.parametrize("Cin,Cout,k,stride,pad,H,W", F16_CASES)
+def test_conv2d_f16_operands_vs_torch_fp32(Cin, Cout, k, stride, pad, H, W):
+    """kb_conv2d with x_f16 (tcgen05 kind::f16: fp16 activations and filters, fp32 accumulate, bias, residual and outputs) against
+    torch fp32 on the SAME fp16-representable operands: only the summation order differs.  Outputs: fp32 raw, fp32 PReLU, fp16 PReLU."""
+    g = torch.Generator().manual_seed(Cin * 1000 + Cout * 7 + k + 1)
+    conv = torch.nn.Conv2d(Cin, Cout, k, stride, pad).cuda()
+    conv.weight.copy_((torch.randn(conv.weight.shape, generator=g) * (2.0 / (Cin * k * k)) ** 0.5).half().float())
+    conv.bias.copy_(torch.randn(Cout, generator=g) * 0.1)
+    x = torch.randn(2, Cin, H, W, generator=g).half().float().cuda()
+    slope = (0.25 + 0.1 * torch.randn(Cout, generator=g)).cuda()
+    ref = conv(x)
+    res = torch.randn(ref.shape, generator=g).cuda()
+    x16 = cs.new_act(2, H, W, Cin, x.device, torch.float16)
+    x16.copy_(x.permute(0, 2, 3, 1))
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    d16 = cs.new_act(2, Ho, Wo, Cout, x.device, torch.float16)
+    outs = cs.conv2d(x16, cs.packed(conv), [(None, False, None), (slope, False, None), (slope, False, d16)], res=nhwc(res))
+    torch.cuda.synchronize()
+    want = ref + res
+    assert outs[2].dtype == torch.float16 and outs[0].dtype == torch.float32
+    assert rel(outs[0].permute(0, 3, 1, 2), want) < 1e-5          # fp32 summation order over K = 9 * Cin only
+    act = torch.nn.functional.prelu(want, slope)
+    assert rel(outs[1].permute(0, 3, 1, 2), act) < 1e-5
+    assert rel(outs[2].permute(0, 3, 1, 2), act.half().float()) < 3e-4          # one fp16 rounding of the stored value

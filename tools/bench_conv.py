@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--n_block", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
     ap.add_argument("--no-cudnn", action="store_true")
+    ap.add_argument("--f16", action="store_true", help="per-layer timings with fp16 operands (kind::f16): fp16 input and output")
     args = ap.parse_args()
     torch.set_grad_enabled(False)
     torch.backends.cudnn.allow_tf32 = True
@@ -69,11 +70,15 @@ def main():
         slope = torch.full((Cout,), 0.25, device=dev)
         pc = cs.packed(conv)
         Ho, Wo = (H + 2 * (k // 2) - k) // stride + 1, (W + 2 * (k // 2) - k) // stride + 1
-        dst = cs.new_act(1, Ho, Wo, Cout, dev)
+        dst = cs.new_act(1, Ho, Wo, Cout, dev, torch.float16 if args.f16 else torch.float32)
+        if args.f16:
+            x16 = cs.new_act(1, H, W, Cin, dev, torch.float16)
+            x16.copy_(xh)
+            xh = x16
         ms = timed(lambda: cs.conv2d(xh, pc, [(slope, True, dst)], tile_w=args.tile_w, n_block=args.n_block,
                                      stages=args.stages), args.iters)
         flops = 2.0 * Cout * Cin * k * k * Ho * Wo
-        out = {"case": f"{Cin}->{Cout} k{k} s{stride} @{H}x{W}", "count_in_inpaint": cnt, "ms": ms,
+        out = {"case": f"{Cin}->{Cout} k{k} s{stride} @{H}x{W}" + (" f16" if args.f16 else ""), "count_in_inpaint": cnt, "ms": ms,
                "tflops": flops / ms / 1e9, "frac_tf32_peak": flops / ms / 1e9 / TF32_PEAK,
                "algorithmic_GBps": 4.0 * (Cin * H * W + Cout * Ho * Wo) / ms / 1e6}
         if not args.no_cudnn:
