@@ -230,6 +230,7 @@ struct ConvKernelParams {
   int debug;            // KB_CONV_DEBUG bit mask (profiling experiments only, see the file header)
   int f16;              // operands are fp16 (activations and packed filters): kind::f16, 64 channels per 128-byte chunk
   int cpc;              // channels per chunk: 32 (tf32) or 64 (f16) -- a chunk is always one 128-byte swizzle row per pixel
+  int fast;             // lean epilogue (epilogue_chunks_lean): dense convolution, Cout % 16 == 0, no per-pixel factors, no debug bits
 };
 
 
@@ -382,6 +383,127 @@ __device__ __forceinline__ void epilogue_rows(const ConvKernelParams &p, const E
 #pragma unroll
       for (int g = 0; g < 4; ++g) rr[g] = rnext[g];
     }
+  }
+}
+
+// ---- the LEAN epilogue of the persistent kernel --------------------------------------------------------------------
+// ncu source page of the 32 -> 32 layer at 768 x 1024 (profiles/ncu_conv_r02v_f16_0_summary.md): nothing on the SM is busy
+// (tensor pipe 12 %, LSU 34 %, issue slots 43 %), yet a tile takes 2 700 cycles -- the time ONE epilogue warp needs for the
+// ~440 dependent instructions epilogue_rows() costs it per tile (16 values per thread): generic-address loads of the
+// shared-memory tables, 64-bit index arithmetic per output and per 4 channels, clamp pairs before the fp16 pack, copies
+// that merge the PReLU / no-PReLU paths.  Two warps per scheduler cannot hide that chain, and dealing tiles to teams of
+// warps does not shorten it.  The common layer (dense convolution, Cout a multiple of 16, no per-pixel factors) takes this
+// form instead: explicit ld.shared of the tables, one address per output, cvt.satfinite for the fp16 pack, the two PReLU
+// cases as separate straight-line paths.  Same arithmetic, same order, bit-identical results.
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// cvt.rna.tf32.f32 for every finite and infinite input in two integer instructions (ptxas expands the cvt into three)
+__device__ __forceinline__ float round_tf32_bits(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
+// two floats -> packed halves (lo in the low 16 bits), saturated to +-65504 like store_half4
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
+  uint32_t h;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
+  return h;
+}
+
+__device__ __forceinline__ void lean_store16(const ConvOut &out, long pix, int c, const float (&w)[16]) {
+  if (out.f16) {
+    uint4 *d = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(out.ptr) + pix * out.stride + c);
+    d[0] = make_uint4(pack_half2_sat(w[0], w[1]), pack_half2_sat(w[2], w[3]), pack_half2_sat(w[4], w[5]), pack_half2_sat(w[6], w[7]));
+    d[1] = make_uint4(pack_half2_sat(w[8], w[9]), pack_half2_sat(w[10], w[11]), pack_half2_sat(w[12], w[13]),
+                      pack_half2_sat(w[14], w[15]));
+  } else {
+    float4 *d = reinterpret_cast<float4 *>(out.ptr + pix * out.stride + c);
+    if (out.round_tf32) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        d[g] = make_float4(round_tf32_bits(w[4 * g]), round_tf32_bits(w[4 * g + 1]), round_tf32_bits(w[4 * g + 2]),
+                           round_tf32_bits(w[4 * g + 3]));
+    } else {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) d[g] = make_float4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+    }
+  }
+}
+
+// A value the epilogue reads every tile, pinned in a register: left to itself the compiler re-reads kernel parameters from the
+// constant bank inside the dependent chains of the tile loop (20-40 cycles each with two warps per scheduler to hide them).
+__device__ __forceinline__ int pin_reg(int v) { asm volatile("" : "+r"(v)); return v; }
+
+// One 16-column chunk of this thread's accumulator row: channels c .. c+15 of pixel `pix`.  `cur` holds the residual of this
+// chunk (loaded one chunk ahead), the residual of the next chunk of this warp (32 channels on) is requested into `nxt`.
+__device__ __forceinline__ void lean_chunk(const ConvKernelParams &p, uint32_t tab, int cpad, int n_out, bool inside, long pix,
+                                           const float *res, uint32_t taddr, int c, bool more, const float4 (&cur)[4],
+                                           float4 (&nxt)[4]) {
+  uint32_t raw[16];
+  tmem_ld16_issue(taddr, raw);
+  if (more && res && inside) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) nxt[g] = *(reinterpret_cast<const float4 *>(res + c + 32) + g);
+  }
+  float4 bs[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) bs[g] = lds_f4(tab + (uint32_t)(c + 4 * g) * 4u);
+  tmem_ld_wait(raw);
+  if (!inside) return;
+  float a[16];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    a[4 * g] = __uint_as_float(raw[4 * g]) + bs[g].x;
+    a[4 * g + 1] = __uint_as_float(raw[4 * g + 1]) + bs[g].y;
+    a[4 * g + 2] = __uint_as_float(raw[4 * g + 2]) + bs[g].z;
+    a[4 * g + 3] = __uint_as_float(raw[4 * g + 3]) + bs[g].w;
+  }
+  if (res) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      a[4 * g] += cur[g].x; a[4 * g + 1] += cur[g].y; a[4 * g + 2] += cur[g].z; a[4 * g + 3] += cur[g].w;
+    }
+  }
+#pragma unroll 1
+  for (int o = 0; o < n_out; ++o) {
+    // `a` is loop-invariant, and the compiler hoists the TF32 rounding and the fp16 pack of the no-PReLU case out of the loop --
+    // 40 instructions per chunk executed whether or not any output wants them.  The empty asm makes `a` opaque per iteration.
+    asm volatile("" : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]), "+f"(a[8]),
+                      "+f"(a[9]), "+f"(a[10]), "+f"(a[11]), "+f"(a[12]), "+f"(a[13]), "+f"(a[14]), "+f"(a[15]));
+    const ConvOut &out = p.out[o];
+    if (out.slope) {
+      const uint32_t st = tab + (uint32_t)((1 + o) * cpad + c) * 4u;
+      float w[16];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float4 sl = lds_f4(st + 16u * g);
+        w[4 * g] = prelu1(a[4 * g], sl.x); w[4 * g + 1] = prelu1(a[4 * g + 1], sl.y);
+        w[4 * g + 2] = prelu1(a[4 * g + 2], sl.z); w[4 * g + 3] = prelu1(a[4 * g + 3], sl.w);
+      }
+      lean_store16(out, pix, c, w);
+    } else {
+      lean_store16(out, pix, c, a);
+    }
+  }
+}
+
+// All 16-column chunks of one accumulator tile that belong to this warp (columns 16*half + 32*i of the N block at n0), two per
+// trip so that the residual buffers swap roles instead of being copied.  `tab` is the shared-memory address of the epilogue
+// tables (bias, then the slopes of output o at (1 + o) * cpad floats); rr holds the residual of the first chunk.
+__device__ __forceinline__ void epilogue_chunks_lean(const ConvKernelParams &p, uint32_t tab, int cpad, int n_out, int Npad, int Cout,
+                                                     bool inside, long pix, uint32_t taddr, int n0, int half, float4 (&rr)[4]) {
+  const float *res = p.res ? p.res + pix * p.res_stride : nullptr;
+  float4 r2[4];
+  int c0 = 16 * half;
+  if (n0 + c0 >= Cout) return;                 // warp-uniform (Cout % 16 == 0: a chunk is whole or absent)
+  for (;;) {
+    bool more = (c0 + 32 < Npad) && (n0 + c0 + 32 < Cout);
+    lean_chunk(p, tab, cpad, n_out, inside, pix, res, taddr + (uint32_t)c0, n0 + c0, more, rr, r2);
+    if (!more) break;
+    c0 += 32;
+    more = (c0 + 32 < Npad) && (n0 + c0 + 32 < Cout);
+    lean_chunk(p, tab, cpad, n_out, inside, pix, res, taddr + (uint32_t)c0, n0 + c0, more, r2, rr);
+    if (!more) break;
+    c0 += 32;
   }
 }
 
@@ -652,6 +774,23 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// All taps of one 128-byte channel chunk, NK K-steps each (NK * 8 tf32 or NK * 16 fp16 channels hold real data), issued by one
+// thread.  A0 / B0: low descriptor words of the halo slice and of the chunk's first filter panel (panels of consecutive taps
+// are b_step_lo apart); acc0 = 0 zeroes the accumulator with the very first MMA.
+template <int KS, bool F16, int NK>
+__device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t A0, uint32_t a_hi, uint32_t B0, uint32_t b_hi, uint32_t idesc,
+                                           uint32_t acc0, uint32_t b_step_lo) {
+  constexpr int kPitch = kHaloTileW + KS - 1;
+#pragma unroll
+  for (int tap = 0; tap < KS * KS; ++tap) {
+    const uint32_t a_off = (uint32_t)(((tap / KS) * kPitch + (tap % KS)) * kChunk * 4) >> 4;   // compile-time
+#pragma unroll
+    for (int k = 0; k < NK; ++k)
+      umma_lh<F16>(d_tmem, A0 + a_off + 2 * k, a_hi, B0 + 2 * k, b_hi, idesc, (tap | k) ? 1u : acc0);
+    B0 += b_step_lo;
+  }
+}
+
 template <int KS, bool F16>
 __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid_constant__ CUtensorMap map_a,
                                                                     const __grid_constant__ CUtensorMap map_b,
@@ -779,19 +918,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
           tc_fence_after();
           const uint32_t A0 = a_tl + a_lo;
           const int ksteps = ck == p.chunks - 1 ? p.last_ksteps : kChunk / 8;   // skip MMA steps made of padding channels only
+          // The issue loop is straight-line code per K-step count: with `if (k < ksteps)` inside one unrolled body the
+          // descriptor arithmetic of the absent steps is still executed (predicated off), and a 32-channel fp16 layer -- two
+          // steps of four -- spent ~110 cycles of issue per MMA the tensor pipe finishes in 64 (profiles/ncu_conv_r02w_f16_0).
           if (leader && !(p.debug & 2)) {
-#pragma unroll
-            for (int tap = 0; tap < kTaps; ++tap) {
-              const uint32_t a_off = (uint32_t)(((tap / KS) * kPitch + (tap % KS)) * kChunk * 4) >> 4;   // compile-time
-#pragma unroll
-              for (int k = 0; k < kChunk / 8; ++k)
-                if (k < ksteps)
-                  umma_lh<F16>(d_tmem, A0 + a_off + 2 * k, a_hi, B0 + 2 * k, b_hi, idesc, (uint32_t)((ck != 0) | (tap != 0) | (k != 0)));
-              B0 += b_step_lo;
-            }
-          } else {
-            B0 += kTaps * b_step_lo;
+            const uint32_t acc0 = (uint32_t)(ck != 0);
+            if (ksteps == 4) issue_taps<KS, F16, 4>(d_tmem, A0, a_hi, B0, b_hi, idesc, acc0, b_step_lo);
+            else if (ksteps == 2) issue_taps<KS, F16, 2>(d_tmem, A0, a_hi, B0, b_hi, idesc, acc0, b_step_lo);
+            else if (ksteps == 1) issue_taps<KS, F16, 1>(d_tmem, A0, a_hi, B0, b_hi, idesc, acc0, b_step_lo);
+            else issue_taps<KS, F16, 3>(d_tmem, A0, a_hi, B0, b_hi, idesc, acc0, b_step_lo);
           }
+          B0 += kTaps * b_step_lo;
           if (leader) umma_commit(a_empty + sa);
           a_lo += kAStage >> 4;
           if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; a_lo = a_base_lo; }
@@ -841,7 +978,32 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
     const EpiSmem es = epi_stage(p, epi_tab, p.cpad, threadIdx.x - 64);
     uint32_t as = 0, phacc = 0;
     TileIter it;
-    for (it.init(p); it.left > 0; it.next(p)) {
+    it.init(p);
+    if (p.fast) {
+      const uint32_t tab = smem_u32(epi_tab);
+      const int Npad = pin_reg(p.Npad), Cout = pin_reg(p.Cout), n_out = pin_reg(p.n_out), cpad = pin_reg(p.cpad);
+      const int Ho = pin_reg(p.Ho), Wo = pin_reg(p.Wo), acc_stages = pin_reg(p.acc_stages);
+      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (; it.left > 0; it.next(p)) {
+        const int n0 = it.nb * Npad, oy = it.ty * kHaloTileH + py, ox = it.tx * kHaloTileW + px;
+        const bool inside = (oy < Ho) & (ox < Wo);
+        const long pix = inside ? ((long)it.img * Ho + oy) * Wo + ox : 0;
+        float4 rr[4];
+        if (p.res && inside && n0 + 16 * half < Cout) {        // in flight while the MMAs of this tile finish
+          const float4 *r4 = reinterpret_cast<const float4 *>(p.res + pix * p.res_stride + n0 + 16 * half);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rr[g] = r4[g];
+        }
+        mbar_wait(acc_full + as, phacc);
+        tc_fence_after();
+        epilogue_chunks_lean(p, tab, cpad, n_out, Npad, Cout, inside, pix, lane_base + as * (uint32_t)Npad, n0, half, rr);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
+        if (++as == (uint32_t)acc_stages) { as = 0; phacc ^= 1u; }
+      }
+    }
+    for (; it.left > 0; it.next(p)) {
       const int n0 = it.nb * p.Npad;
       const EpiPixel ep = epi_pixel(p, it.img, it.ty * kHaloTileH + py, it.tx * kHaloTileW + px);
       float4 rr[4];
@@ -1314,6 +1476,9 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
   const int halo_w = kHaloTileW + a->ksize - 1, halo_h = kHaloTileH + a->ksize - 1;
   p.pitch = halo_w;
   p.debug = env_int("KB_CONV_DEBUG", 0);
+  p.fast = (p.debug == 0 && a->Cout % 16 == 0 && !a->pc_ratio && !env_int("KB_CONV_NO_LEAN", 0)) ? 1 : 0;
+  for (int o = 0; o < a->n_out; ++o)
+    if (a->out[o].mul) p.fast = 0;
   const int box_bytes = p.pitch * halo_h * kChunk * 4;
   p.a_stage_bytes = (box_bytes + 1023) & ~1023;
   p.acc_stages = min(kAccMax, 512 / npad);
