@@ -189,6 +189,7 @@ constexpr int kTileM = 128;            // output pixels per CTA = UMMA M
 constexpr int kChunk = 32;             // input channels per K step (32 fp32 = one 128-byte swizzle row)
 constexpr int kABytes = kTileM * kChunk * 4;
 constexpr int kConvThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int kHaloMaxThreads = 448;   // persistent kernel with the lean epilogue: up to three teams of four epilogue warps
 constexpr int kMaxOut = 3;
 
 struct ConvOut {
@@ -198,6 +199,7 @@ struct ConvOut {
   const float *mul;     // per-pixel factor applied last (the {0,1} mask a partial-conv consumer multiplies its input with)
   int round_tf32;       // round to TF32 (the value only feeds convolutions)
   int f16;              // store as fp16 (ptr points at halves, stride counts halves): the input of a kind::f16 convolution
+  int wide;             // every pixel of this output starts on a 32-byte boundary: the lean epilogue stores 32 bytes per instruction
 };
 
 struct ConvKernelParams {
@@ -231,6 +233,7 @@ struct ConvKernelParams {
   int f16;              // operands are fp16 (activations and packed filters): kind::f16, 64 channels per 128-byte chunk
   int cpc;              // channels per chunk: 32 (tf32) or 64 (f16) -- a chunk is always one 128-byte swizzle row per pixel
   int fast;             // lean epilogue (epilogue_chunks_lean): dense convolution, Cout % 16 == 0, no per-pixel factors, no debug bits
+  int teams;            // lean epilogue: teams of 4 warps, team t takes tiles t, t + teams, ... of the CTA (block = 64 + 128 * teams threads)
 };
 
 
@@ -267,19 +270,19 @@ struct EpiSmem {
 // floats of shared memory the epilogue tables take for `cpad` (padded) output channels
 __host__ __device__ constexpr int epi_smem_floats(int cpad) { return (1 + kMaxOut) * cpad; }
 
-// Called by all 256 epilogue threads (tid 0..255) before their first tile; ends with a barrier among them.
-__device__ __forceinline__ EpiSmem epi_stage(const ConvKernelParams &p, float *base, int cpad, int tid) {
+// Called by all nthr epilogue threads (tid 0..nthr-1) before their first tile; ends with a barrier among them.
+__device__ __forceinline__ EpiSmem epi_stage(const ConvKernelParams &p, float *base, int cpad, int tid, int nthr = 256) {
   EpiSmem e;
   e.bias = base;
   e.cpad = cpad;
-  for (int c = tid; c < cpad; c += 256) base[c] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+  for (int c = tid; c < cpad; c += nthr) base[c] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
 #pragma unroll
   for (int o = 0; o < kMaxOut; ++o) {
     float *dst = base + (1 + o) * cpad;
     if (o < p.n_out && p.out[o].slope)
-      for (int c = tid; c < cpad; c += 256) dst[c] = c < p.Cout ? __ldg(p.out[o].slope + c) : 1.f;
+      for (int c = tid; c < cpad; c += nthr) dst[c] = c < p.Cout ? __ldg(p.out[o].slope + c) : 1.f;
   }
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+  asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
   return e;
 }
 
@@ -409,22 +412,45 @@ __device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
   return h;
 }
 
+// 32 bytes in one instruction (sm_100 has 256-bit global accesses).  With two 16-byte stores per 32-byte sector the layer ran at
+// the speed of its stores: every warp-level store touches 32 different lines (one per pixel), each sector arrives in L2 in two
+// halves, and with MMAs and loads switched off (KB_CONV_DEBUG=6) the 32 -> 32 layer still took 25 us (fp16 output) / 40 us (fp32
+// output) of the 37 / 56 us of the whole kernel.
+__device__ __forceinline__ void stg256(void *ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g,
+                                       uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f),
+               "r"(g), "r"(h)
+               : "memory");
+}
+
 __device__ __forceinline__ void lean_store16(const ConvOut &out, long pix, int c, const float (&w)[16]) {
   if (out.f16) {
     uint4 *d = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(out.ptr) + pix * out.stride + c);
-    d[0] = make_uint4(pack_half2_sat(w[0], w[1]), pack_half2_sat(w[2], w[3]), pack_half2_sat(w[4], w[5]), pack_half2_sat(w[6], w[7]));
-    d[1] = make_uint4(pack_half2_sat(w[8], w[9]), pack_half2_sat(w[10], w[11]), pack_half2_sat(w[12], w[13]),
-                      pack_half2_sat(w[14], w[15]));
+    const uint32_t h0 = pack_half2_sat(w[0], w[1]), h1 = pack_half2_sat(w[2], w[3]), h2 = pack_half2_sat(w[4], w[5]),
+                   h3 = pack_half2_sat(w[6], w[7]), h4 = pack_half2_sat(w[8], w[9]), h5 = pack_half2_sat(w[10], w[11]),
+                   h6 = pack_half2_sat(w[12], w[13]), h7 = pack_half2_sat(w[14], w[15]);
+    if (out.wide) {
+      stg256(d, h0, h1, h2, h3, h4, h5, h6, h7);
+    } else {
+      d[0] = make_uint4(h0, h1, h2, h3);
+      d[1] = make_uint4(h4, h5, h6, h7);
+    }
   } else {
     float4 *d = reinterpret_cast<float4 *>(out.ptr + pix * out.stride + c);
+    uint32_t v[16];
     if (out.round_tf32) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
-        d[g] = make_float4(round_tf32_bits(w[4 * g]), round_tf32_bits(w[4 * g + 1]), round_tf32_bits(w[4 * g + 2]),
-                           round_tf32_bits(w[4 * g + 3]));
+      for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(round_tf32_bits(w[i]));
     } else {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) d[g] = make_float4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+      for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(w[i]);
+    }
+    if (out.wide) {
+      stg256(d, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+      stg256(d + 2, v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
+    } else {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) reinterpret_cast<uint4 *>(d)[g] = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
     }
   }
 }
@@ -434,7 +460,7 @@ __device__ __forceinline__ void lean_store16(const ConvOut &out, long pix, int c
 __device__ __forceinline__ int pin_reg(int v) { asm volatile("" : "+r"(v)); return v; }
 
 // One 16-column chunk of this thread's accumulator row: channels c .. c+15 of pixel `pix`.  `cur` holds the residual of this
-// chunk (loaded one chunk ahead), the residual of the next chunk of this warp (32 channels on) is requested into `nxt`.
+// chunk (loaded one chunk ahead), the residual of the next chunk (16 channels on) is requested into `nxt`.
 __device__ __forceinline__ void lean_chunk(const ConvKernelParams &p, uint32_t tab, int cpad, int n_out, bool inside, long pix,
                                            const float *res, uint32_t taddr, int c, bool more, const float4 (&cur)[4],
                                            float4 (&nxt)[4]) {
@@ -442,7 +468,7 @@ __device__ __forceinline__ void lean_chunk(const ConvKernelParams &p, uint32_t t
   tmem_ld16_issue(taddr, raw);
   if (more && res && inside) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) nxt[g] = *(reinterpret_cast<const float4 *>(res + c + 32) + g);
+    for (int g = 0; g < 4; ++g) nxt[g] = *(reinterpret_cast<const float4 *>(res + c + 16) + g);
   }
   float4 bs[4];
 #pragma unroll
@@ -486,24 +512,24 @@ __device__ __forceinline__ void lean_chunk(const ConvKernelParams &p, uint32_t t
   }
 }
 
-// All 16-column chunks of one accumulator tile that belong to this warp (columns 16*half + 32*i of the N block at n0), two per
-// trip so that the residual buffers swap roles instead of being copied.  `tab` is the shared-memory address of the epilogue
-// tables (bias, then the slopes of output o at (1 + o) * cpad floats); rr holds the residual of the first chunk.
+// All 16-column chunks of one accumulator tile that belong to this warp: columns 0, 16, 32, ... of the N block at n0 (a team
+// of four warps owns a tile, one warp per TMEM lane quadrant), two chunks per trip so that the residual buffers swap roles
+// instead of being copied.  `tab` is the shared-memory address of the epilogue tables (bias, then the slopes of output o at
+// (1 + o) * cpad floats); rr holds the residual of the first chunk.
 __device__ __forceinline__ void epilogue_chunks_lean(const ConvKernelParams &p, uint32_t tab, int cpad, int n_out, int Npad, int Cout,
-                                                     bool inside, long pix, uint32_t taddr, int n0, int half, float4 (&rr)[4]) {
+                                                     bool inside, long pix, uint32_t taddr, int n0, float4 (&rr)[4]) {
   const float *res = p.res ? p.res + pix * p.res_stride : nullptr;
   float4 r2[4];
-  int c0 = 16 * half;
-  if (n0 + c0 >= Cout) return;                 // warp-uniform (Cout % 16 == 0: a chunk is whole or absent)
+  int c0 = 0;
   for (;;) {
-    bool more = (c0 + 32 < Npad) && (n0 + c0 + 32 < Cout);
+    bool more = (c0 + 16 < Npad) && (n0 + c0 + 16 < Cout);        // warp-uniform (Cout % 16 == 0: a chunk is whole or absent)
     lean_chunk(p, tab, cpad, n_out, inside, pix, res, taddr + (uint32_t)c0, n0 + c0, more, rr, r2);
     if (!more) break;
-    c0 += 32;
-    more = (c0 + 32 < Npad) && (n0 + c0 + 32 < Cout);
+    c0 += 16;
+    more = (c0 + 16 < Npad) && (n0 + c0 + 16 < Cout);
     lean_chunk(p, tab, cpad, n_out, inside, pix, res, taddr + (uint32_t)c0, n0 + c0, more, r2, rr);
     if (!more) break;
-    c0 += 32;
+    c0 += 16;
   }
 }
 
@@ -741,8 +767,9 @@ struct TileIter {
   int nb, tx, ty, img;
   int d_nb, d_tx, d_ty, d_img;
   int left;
-  __device__ __forceinline__ void init(const ConvKernelParams &p) {
-    long w = blockIdx.x, step = gridDim.x;
+  // visits w = blockIdx.x + first * gridDim.x, += every * gridDim.x, ...
+  __device__ __forceinline__ void init(const ConvKernelParams &p, int first = 0, int every = 1) {
+    long w = blockIdx.x + (long)first * gridDim.x, step = (long)every * gridDim.x;
     left = w < p.work_items ? (int)((p.work_items - w + step - 1) / step) : 0;
     nb = (int)(w % p.n_blocks); w /= p.n_blocks;
     tx = (int)(w % p.tiles_x); w /= p.tiles_x;
@@ -792,7 +819,7 @@ __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t A0, uint32_
 }
 
 template <int KS, bool F16>
-__global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(kHaloMaxThreads, 1) k_conv_halo_tf32(const __grid_constant__ CUtensorMap map_a,
                                                                     const __grid_constant__ CUtensorMap map_b,
                                                                     const ConvKernelParams p) {
   constexpr int kTaps = KS * KS;
@@ -821,7 +848,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-    for (int s = 0; s < kAccMax; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 8); }
+    for (int s = 0; s < kAccMax; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, p.fast ? 4 : 8); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -975,33 +1002,41 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_halo_tf32(const __grid
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int m = q * 32 + lane;
     const int py = m / kHaloTileW, px = m - py * kHaloTileW;
-    const EpiSmem es = epi_stage(p, epi_tab, p.cpad, threadIdx.x - 64);
+    const EpiSmem es = epi_stage(p, epi_tab, p.cpad, threadIdx.x - 64, (int)blockDim.x - 64);
     uint32_t as = 0, phacc = 0;
     TileIter it;
-    it.init(p);
     if (p.fast) {
+      // Teams of four warps (one per TMEM lane quadrant), team t on tiles t, t + teams, ...: the per-tile bookkeeping of a warp
+      // (tile coordinates, pixel index, barrier wait) is paid once for all the chunks of its rows, and `teams` tiles are in
+      // flight, which is what hides the latency of each warp's dependent chain (two or three warps per scheduler).
+      const int team = (warp - 2) >> 2, teams = pin_reg(p.teams);
       const uint32_t tab = smem_u32(epi_tab);
       const int Npad = pin_reg(p.Npad), Cout = pin_reg(p.Cout), n_out = pin_reg(p.n_out), cpad = pin_reg(p.cpad);
       const int Ho = pin_reg(p.Ho), Wo = pin_reg(p.Wo), acc_stages = pin_reg(p.acc_stages);
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-      for (; it.left > 0; it.next(p)) {
+      as = (uint32_t)team;
+      while (as >= (uint32_t)acc_stages) { as -= acc_stages; phacc ^= 1u; }
+      for (it.init(p, team, teams); it.left > 0; it.next(p)) {
         const int n0 = it.nb * Npad, oy = it.ty * kHaloTileH + py, ox = it.tx * kHaloTileW + px;
         const bool inside = (oy < Ho) & (ox < Wo);
         const long pix = inside ? ((long)it.img * Ho + oy) * Wo + ox : 0;
         float4 rr[4];
-        if (p.res && inside && n0 + 16 * half < Cout) {        // in flight while the MMAs of this tile finish
-          const float4 *r4 = reinterpret_cast<const float4 *>(p.res + pix * p.res_stride + n0 + 16 * half);
+        if (p.res && inside) {                                 // in flight while the MMAs of this tile finish
+          const float4 *r4 = reinterpret_cast<const float4 *>(p.res + pix * p.res_stride + n0);
 #pragma unroll
           for (int g = 0; g < 4; ++g) rr[g] = r4[g];
         }
         mbar_wait(acc_full + as, phacc);
         tc_fence_after();
-        epilogue_chunks_lean(p, tab, cpad, n_out, Npad, Cout, inside, pix, lane_base + as * (uint32_t)Npad, n0, half, rr);
+        epilogue_chunks_lean(p, tab, cpad, n_out, Npad, Cout, inside, pix, lane_base + as * (uint32_t)Npad, n0, rr);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
-        if (++as == (uint32_t)acc_stages) { as = 0; phacc ^= 1u; }
+        as += (uint32_t)teams;
+        while (as >= (uint32_t)acc_stages) { as -= acc_stages; phacc ^= 1u; }
       }
+    } else {
+      it.init(p);
     }
     for (; it.left > 0; it.next(p)) {
       const int n0 = it.nb * p.Npad;
@@ -1441,6 +1476,8 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
     p.out[o].mul = a->out[o].mul;
     p.out[o].round_tf32 = a->out[o].round_tf32;
     p.out[o].f16 = a->out[o].store_f16;
+    p.out[o].wide = (reinterpret_cast<uintptr_t>(a->out[o].ptr) & 31) == 0 &&
+                    (a->out[o].pixel_stride * (a->out[o].store_f16 ? 2 : 4)) % 32 == 0 && !env_int("KB_CONV_NO_WIDE", 0);
   }
   KB_REQUIRE((a->pc_ratio == nullptr) == (a->pc_um == nullptr), "kb_conv2d: pc_ratio and pc_um come together");
   p.pc_ratio = a->pc_ratio;
@@ -1476,13 +1513,16 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
   const int halo_w = kHaloTileW + a->ksize - 1, halo_h = kHaloTileH + a->ksize - 1;
   p.pitch = halo_w;
   p.debug = env_int("KB_CONV_DEBUG", 0);
-  p.fast = (p.debug == 0 && a->Cout % 16 == 0 && !a->pc_ratio && !env_int("KB_CONV_NO_LEAN", 0)) ? 1 : 0;
+  p.fast = ((p.debug & ~6) == 0 && a->Cout % 16 == 0 && !a->pc_ratio && !env_int("KB_CONV_NO_LEAN", 0)) ? 1 : 0;
   for (int o = 0; o < a->n_out; ++o)
     if (a->out[o].mul) p.fast = 0;
   const int box_bytes = p.pitch * halo_h * kChunk * 4;
   p.a_stage_bytes = (box_bytes + 1023) & ~1023;
   p.acc_stages = min(kAccMax, 512 / npad);
   KB_REQUIRE(p.acc_stages >= 2, "kb_conv2d: accumulator does not fit TMEM");
+  // a team's first wait must be for the first phase of its accumulator stage: teams <= acc_stages
+  p.teams = p.fast ? max(1, min(min(env_int("KB_CONV_TEAMS", 3), 3), p.acc_stages)) : 0;
+  const int halo_threads = p.fast ? 64 + 128 * p.teams : kConvThreads;
   p.tmem_cols = (uint32_t)max(32, pow2_at_least(p.acc_stages * npad));
   const size_t bar_bytes = 1024;                         // barriers + TMEM slot
   const size_t fixed = 1024 + bar_bytes + epi_bytes;     // alignment slack + barriers + epilogue tables
@@ -1507,11 +1547,11 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
   KB_REQUIRE(smem <= smem_cap, "kb_conv2d: pipeline does not fit shared memory");
   const unsigned grid = (unsigned)min((long)sm_count(), p.work_items);
   if (a->ksize == 1) {
-    if (p.f16) k_conv_halo_tf32<1, true><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
-    else k_conv_halo_tf32<1, false><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+    if (p.f16) k_conv_halo_tf32<1, true><<<grid, halo_threads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+    else k_conv_halo_tf32<1, false><<<grid, halo_threads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
   } else {
-    if (p.f16) k_conv_halo_tf32<3, true><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
-    else k_conv_halo_tf32<3, false><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+    if (p.f16) k_conv_halo_tf32<3, true><<<grid, halo_threads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+    else k_conv_halo_tf32<3, false><<<grid, halo_threads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
   }
   count_launch();
   return check_launch("kb_conv2d");

@@ -2,6 +2,7 @@
 // independent TMEM accumulators the issue loop rotates over.  One CTA per SM, one issuing thread.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_rate umma_rate.cu ; run on the GPU box.
 #include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -69,7 +70,8 @@ __global__ void k(int N, int nacc, int reps, uint32_t sbo, int a_off, long long 
 // slices of 9 resident 4 KB panels), accumulating into one TMEM accumulator per tile, 4 accumulators in rotation.
 // bg: 0 none, 1 eight other warps stream 128-bit shared-memory LOADS (the epilogue's bias / slope tables), 2 they stream 128-bit
 // shared-memory STORES into an unrelated region (stand-in for TMA writes of the next halo tiles).
-template <int KIND>
+// KSTEPS: K-steps issued per tap (4 = a full 128-byte chunk; 2 = the 32-channel fp16 layer, half of every 128-byte row is padding)
+template <int KIND, int KSTEPS>
 __global__ void kconv(int N, int tiles, int bg, long long *out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -105,7 +107,8 @@ __global__ void kconv(int N, int tiles, int bg, long long *out) {
     for (int t = 0; t < tiles; ++t) {
       const uint32_t d = tm + (uint32_t)((t & 3) * N);
 #pragma unroll
-      for (int i = 0; i < 36; ++i) mma<KIND>(d, da[i], db[i], idesc, i != 0);
+      for (int i = 0; i < 36; ++i)
+        if ((i & 3) < KSTEPS) mma<KIND>(d, da[i], db[i], idesc, i != 0);
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
     asm volatile("{\n.reg .pred p;\nW2:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra D2;\nbra W2;\nD2:\n}" ::"r"(smem_u32(&bar)) : "memory");
@@ -134,6 +137,23 @@ __global__ void kconv(int N, int tiles, int bg, long long *out) {
   if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512) : "memory");
 }
 
+template <int KIND, int KSTEPS>
+static void run_conv(long long *out) {
+  cudaFuncSetAttribute(kconv<KIND, KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
+  for (int N : {32, 64})
+    for (int bg = 0; bg < 3; ++bg) {
+      const int tiles = 128;
+      for (int it = 0; it < 2; ++it) {
+        kconv<KIND, KSTEPS><<<148, 320, 132 * 1024>>>(N, tiles, bg, out);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); exit(1); }
+      }
+      printf("{\"pattern\": \"conv 9 taps x %d k-steps, %d MMAs per accumulator\", \"kind\": \"%s\", \"N\": %d, \"background\": \"%s\", \"cycles_per_mma\": %.1f, \"cycles_per_tap\": %.1f}\n",
+             KSTEPS, 9 * KSTEPS, KIND ? "bf16" : "tf32", N, bg == 0 ? "none" : (bg == 1 ? "8 warps of 128-bit shared loads" : "8 warps of 128-bit shared stores"),
+             (double)out[0] / (tiles * 9 * KSTEPS), (double)out[0] / (tiles * 9));
+    }
+}
+
 int main() {
   long long *out;
   cudaMallocManaged(&out, 8);
@@ -157,21 +177,8 @@ int main() {
                  kind ? "bf16" : "tf32", N, nacc, variant, (double)out[0] / reps, N / 2);
         }
       }
-  cudaFuncSetAttribute(kconv<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
-  cudaFuncSetAttribute(kconv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
-  for (int kind = 0; kind < 2; ++kind)
-    for (int N : {32, 64})
-      for (int bg = 0; bg < 3; ++bg) {
-        const int tiles = 128;
-        for (int it = 0; it < 2; ++it) {
-          if (kind == 0) kconv<0><<<148, 320, 132 * 1024>>>(N, tiles, bg, out);
-          else kconv<1><<<148, 320, 132 * 1024>>>(N, tiles, bg, out);
-          cudaError_t e = cudaDeviceSynchronize();
-          if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
-        }
-        printf("{\"pattern\": \"conv 9 taps x 4 k-steps, 36 MMAs per accumulator\", \"kind\": \"%s\", \"N\": %d, \"background\": \"%s\", \"cycles_per_mma\": %.1f}\n",
-               kind ? "bf16" : "tf32", N, bg == 0 ? "none" : (bg == 1 ? "8 warps of 128-bit shared loads" : "8 warps of 128-bit shared stores"),
-               (double)out[0] / (tiles * 36));
-      }
+  run_conv<0, 4>(out); run_conv<1, 4>(out);
+  // fewer K-steps per tap: what one tap costs when only part of each 128-byte row is consumed
+  run_conv<1, 2>(out); run_conv<1, 1>(out); run_conv<0, 2>(out); run_conv<0, 1>(out);
   return 0;
 }
