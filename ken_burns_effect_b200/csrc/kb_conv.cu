@@ -189,7 +189,10 @@ constexpr int kTileM = 128;            // output pixels per CTA = UMMA M
 constexpr int kChunk = 32;             // input channels per K step (32 fp32 = one 128-byte swizzle row)
 constexpr int kABytes = kTileM * kChunk * 4;
 constexpr int kConvThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
-constexpr int kHaloMaxThreads = 448;   // persistent kernel with the lean epilogue: up to three teams of four epilogue warps
+// persistent kernel: warp 0 TMA, warps 1-2 MMA issuers, then the epilogue warps (8 with the generic epilogue, teams of 4 with the lean one)
+constexpr int kHaloIssuers = 2, kHaloEpiWarp0 = 1 + kHaloIssuers;
+constexpr int kHaloThreads = 32 * kHaloEpiWarp0 + 256;        // generic epilogue
+constexpr int kHaloMaxThreads = 32 * kHaloEpiWarp0 + 3 * 128;   // lean epilogue: up to three teams
 constexpr int kMaxOut = 3;
 
 struct ConvOut {
@@ -233,7 +236,10 @@ struct ConvKernelParams {
   int f16;              // operands are fp16 (activations and packed filters): kind::f16, 64 channels per 128-byte chunk
   int cpc;              // channels per chunk: 32 (tf32) or 64 (f16) -- a chunk is always one 128-byte swizzle row per pixel
   int fast;             // lean epilogue (epilogue_chunks_lean): dense convolution, Cout % 16 == 0, no per-pixel factors, no debug bits
-  int teams;            // lean epilogue: teams of 4 warps, team t takes tiles t, t + teams, ... of the CTA (block = 64 + 128 * teams threads)
+  int res_wide;         // every pixel of the residual starts on a 32-byte boundary
+  int issuers;          // MMA-issuing warps: 2 with resident filters (items alternate; each issuer has its own half of the
+                        // activation ring, its own accumulator stages and its own epilogue team), else 1
+  int teams;            // lean epilogue: teams of 4 warps, team t takes tiles t, t + teams, ... of the CTA (block = 96 + 128 * teams threads)
 };
 
 
@@ -423,6 +429,22 @@ __device__ __forceinline__ void stg256(void *ptr, uint32_t a, uint32_t b, uint32
                : "memory");
 }
 
+// 16 consecutive floats of the residual: two 32-byte loads when the pixel starts on a 32-byte boundary, else four 16-byte ones
+__device__ __forceinline__ void lean_load_res(const float *src, bool wide, float4 (&r)[4]) {
+  if (wide) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=f"(r[2 * h].x), "=f"(r[2 * h].y), "=f"(r[2 * h].z), "=f"(r[2 * h].w), "=f"(r[2 * h + 1].x),
+                     "=f"(r[2 * h + 1].y), "=f"(r[2 * h + 1].z), "=f"(r[2 * h + 1].w)
+                   : "l"(src + 8 * h)
+                   : "memory");
+  } else {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) r[g] = *(reinterpret_cast<const float4 *>(src) + g);
+  }
+}
+
 __device__ __forceinline__ void lean_store16(const ConvOut &out, long pix, int c, const float (&w)[16]) {
   if (out.f16) {
     uint4 *d = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(out.ptr) + pix * out.stride + c);
@@ -466,10 +488,7 @@ __device__ __forceinline__ void lean_chunk(const ConvKernelParams &p, uint32_t t
                                            float4 (&nxt)[4]) {
   uint32_t raw[16];
   tmem_ld16_issue(taddr, raw);
-  if (more && res && inside) {
-#pragma unroll
-    for (int g = 0; g < 4; ++g) nxt[g] = *(reinterpret_cast<const float4 *>(res + c + 16) + g);
-  }
+  if (more && res && inside) lean_load_res(res + c + 16, p.res_wide != 0, nxt);
   float4 bs[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) bs[g] = lds_f4(tab + (uint32_t)(c + 4 * g) * 4u);
@@ -860,7 +879,13 @@ __global__ void __launch_bounds__(kHaloMaxThreads, 1) k_conv_halo_tf32(const __g
   if (warp == 0) {
     // ===== TMA producer (whole warp, one elected lane issues) =====
     const bool leader = elect_one();
-    uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
+    uint32_t sb = 0, phb = 0;
+    // activation ring(s): one per MMA issuer (ring r = slots r * ring .. + ring - 1), items alternate between them.  Every barrier
+    // then has one producer and one consumer that visit all of its phases in order; with a shared ring an issuer would wait for
+    // a phase two ahead of the last one it saw, which a parity wait cannot tell from "already complete".
+    const uint32_t ring = (uint32_t)(p.a_stages / p.issuers);
+    uint32_t ra[2] = {0, 0}, rph[2] = {0, 0};
+    uint32_t par = 0;
     bool first = true;
     TileIter it;
     it.init(p);
@@ -887,6 +912,8 @@ __global__ void __launch_bounds__(kHaloMaxThreads, 1) k_conv_halo_tf32(const __g
       const int img = it.img;
       const int cx = it.tx * kHaloTileW - p.pad, cy = it.ty * kHaloTileH - p.pad, cn = it.nb * p.Npad;
       for (int ck = 0; ck < p.chunks; ++ck) {
+        const uint32_t pos = par ? ra[1] : ra[0], pha = par ? rph[1] : rph[0];
+        const uint32_t sa = par * ring + pos;
         mbar_wait(a_empty + sa, pha ^ 1u);
         if (leader) {
           if (p.debug & 4) {   // experiment: no activation loads, barriers only
@@ -896,7 +923,9 @@ __global__ void __launch_bounds__(kHaloMaxThreads, 1) k_conv_halo_tf32(const __g
             tma_load_4d(&map_a, a_full + sa, smem_a + (size_t)sa * kAStage, ck * p.cpc, cx, cy, img);
           }
         }
-        if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; }
+        const bool wrap = pos + 1 == ring;
+        if (par) { ra[1] = wrap ? 0 : pos + 1; rph[1] ^= wrap ? 1u : 0u; }
+        else { ra[0] = wrap ? 0 : pos + 1; rph[0] ^= wrap ? 1u : 0u; }
         if (!p.resident || first) {
           int j = ck;                                   // packed weights: panel (tap, ck) at index tap*chunks + ck
           for (int tap = 0; tap < kTaps; ++tap, j += p.chunks) {
@@ -910,9 +939,10 @@ __global__ void __launch_bounds__(kHaloMaxThreads, 1) k_conv_halo_tf32(const __g
         }
       }
       first = false;
+      if (p.issuers == 2) par ^= 1u;
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
+  } else if (warp < kHaloEpiWarp0) {
+    // ===== MMA issuers =====
     // The WHOLE warp runs this loop and one elected lane issues the tcgen05 instructions.  With the loop inside
     // `if (lane == 0)` the compiler keeps the ring state in per-thread registers and moves every descriptor into uniform
     // registers one MMA at a time: ncu showed ~17 dependent instructions (~128 cycles) per MMA on the issuing thread, i.e.
@@ -924,30 +954,41 @@ __global__ void __launch_bounds__(kHaloMaxThreads, 1) k_conv_halo_tf32(const __g
     const uint32_t a_hi = (uint32_t)(tmpl_a >> 32), b_hi = (uint32_t)(tmpl_b >> 32);
     const uint32_t a_tl = (uint32_t)tmpl_a, b_tl = (uint32_t)tmpl_b;          // low words without the address field
     const uint32_t a_base_lo = smem_u32(smem_a) >> 4, b_base_lo = smem_u32(smem_b) >> 4, b_step_lo = (uint32_t)b_bytes >> 4;
-    uint32_t sa = 0, pha = 0, a_lo = a_base_lo;
+    uint32_t sa = 0, pha = 0, a_lo = a_base_lo;                 // (a position inside the issuer's own ring when filters are resident)
     uint32_t sb = 0, phb = 0, b_lo = b_base_lo;
     uint32_t as = 0, phacc = 0;
     const int n_items = blockIdx.x < p.work_items ? (int)((p.work_items - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
     // Shared-memory addresses fit the 14-bit (>> 4) address field, whose bits are zero in the templates: "template | address"
     // is "template + address", and the step from one MMA to the next is a compile-time constant added to a per-slot base.
     if (p.resident) {
-      // filters stay in shared memory: wait once for all panels, then the loop has no weight bookkeeping at all
+      // Filters stay in shared memory: wait once for all panels, then the loop has no weight bookkeeping at all.
+      // TWO issuing warps, items alternating between them.  The tensor core's queue is short: while a single issuer ran its
+      // per-tile bookkeeping (two barrier waits, fences, two commits, ring arithmetic: ~500 cycles of dependent latency) the
+      // queue drained, and a 32 -> 32 fp16 tile took 1 650 cycles for 18 MMAs the pipe finishes in 860
+      // (tools/micro/umma_rate.cu, 2 K-steps per tap).  With two issuers one's bookkeeping overlaps the other's MMAs; the tiles
+      // are independent (own accumulator stages, own activation ring, own epilogue team) and a commit tracks the MMAs of its own
+      // thread only.  MMAs of different issuers may complete out of order, which is why nothing is shared between the two chains.
+      const int issuer = warp - 1;
+      if (issuer < p.issuers) {
       if (n_items > 0)
         for (int j = 0; j < p.b_stages; ++j) mbar_wait(b_full + j, 0);
       tc_fence_after();
-      for (int item = 0; item < n_items; ++item) {
+      const uint32_t ring = (uint32_t)(p.a_stages / p.issuers), slot0 = (uint32_t)issuer * ring;
+      const uint32_t a_step_lo = kAStage >> 4;
+      as = (uint32_t)issuer;                                  // accumulator stages issuer, issuer + issuers, ... (acc_stages is even)
+      for (int item = issuer; item < n_items; item += p.issuers) {
         mbar_wait(acc_empty + as, phacc ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * (uint32_t)p.Npad;
         uint32_t B0 = b_tl + b_base_lo;                       // panel (ck, tap) at slot ck * taps + tap
         for (int ck = 0; ck < p.chunks; ++ck) {
-          mbar_wait(a_full + sa, pha);
+          mbar_wait(a_full + slot0 + sa, pha);
           tc_fence_after();
-          const uint32_t A0 = a_tl + a_lo;
+          const uint32_t A0 = a_tl + a_base_lo + (slot0 + sa) * a_step_lo;
           const int ksteps = ck == p.chunks - 1 ? p.last_ksteps : kChunk / 8;   // skip MMA steps made of padding channels only
           // The issue loop is straight-line code per K-step count: with `if (k < ksteps)` inside one unrolled body the
           // descriptor arithmetic of the absent steps is still executed (predicated off), and a 32-channel fp16 layer -- two
-          // steps of four -- spent ~110 cycles of issue per MMA the tensor pipe finishes in 64 (profiles/ncu_conv_r02w_f16_0).
+          // steps of four -- spent ~110 cycles of issue per MMA (profiles/ncu_conv_r02w_f16_0).
           if (leader && !(p.debug & 2)) {
             const uint32_t acc0 = (uint32_t)(ck != 0);
             if (ksteps == 4) issue_taps<KS, F16, 4>(d_tmem, A0, a_hi, B0, b_hi, idesc, acc0, b_step_lo);
@@ -956,14 +997,15 @@ __global__ void __launch_bounds__(kHaloMaxThreads, 1) k_conv_halo_tf32(const __g
             else issue_taps<KS, F16, 3>(d_tmem, A0, a_hi, B0, b_hi, idesc, acc0, b_step_lo);
           }
           B0 += kTaps * b_step_lo;
-          if (leader) umma_commit(a_empty + sa);
-          a_lo += kAStage >> 4;
-          if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; a_lo = a_base_lo; }
+          if (leader) umma_commit(a_empty + slot0 + sa);
+          if (++sa == ring) { sa = 0; pha ^= 1u; }
         }
         if (leader) umma_commit(acc_full + as);
-        if (++as == (uint32_t)p.acc_stages) { as = 0; phacc ^= 1u; }
+        as += (uint32_t)p.issuers;
+        if (as >= (uint32_t)p.acc_stages) { as -= p.acc_stages; phacc ^= 1u; }
       }
-    } else {
+      }
+    } else if (warp == 1) {
       for (int item = 0; item < n_items; ++item) {
         mbar_wait(acc_empty + as, phacc ^ 1u);
         tc_fence_after();
@@ -999,17 +1041,17 @@ __global__ void __launch_bounds__(kHaloMaxThreads, 1) k_conv_halo_tf32(const __g
     }
   } else {
     // ===== epilogue warps =====
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int q = warp & 3, half = (warp - kHaloEpiWarp0) >> 2;
     const int m = q * 32 + lane;
     const int py = m / kHaloTileW, px = m - py * kHaloTileW;
-    const EpiSmem es = epi_stage(p, epi_tab, p.cpad, threadIdx.x - 64, (int)blockDim.x - 64);
+    const EpiSmem es = epi_stage(p, epi_tab, p.cpad, threadIdx.x - 32 * kHaloEpiWarp0, (int)blockDim.x - 32 * kHaloEpiWarp0);
     uint32_t as = 0, phacc = 0;
     TileIter it;
     if (p.fast) {
       // Teams of four warps (one per TMEM lane quadrant), team t on tiles t, t + teams, ...: the per-tile bookkeeping of a warp
       // (tile coordinates, pixel index, barrier wait) is paid once for all the chunks of its rows, and `teams` tiles are in
       // flight, which is what hides the latency of each warp's dependent chain (two or three warps per scheduler).
-      const int team = (warp - 2) >> 2, teams = pin_reg(p.teams);
+      const int team = (warp - kHaloEpiWarp0) >> 2, teams = pin_reg(p.teams);
       const uint32_t tab = smem_u32(epi_tab);
       const int Npad = pin_reg(p.Npad), Cout = pin_reg(p.Cout), n_out = pin_reg(p.n_out), cpad = pin_reg(p.cpad);
       const int Ho = pin_reg(p.Ho), Wo = pin_reg(p.Wo), acc_stages = pin_reg(p.acc_stages);
@@ -1021,11 +1063,7 @@ __global__ void __launch_bounds__(kHaloMaxThreads, 1) k_conv_halo_tf32(const __g
         const bool inside = (oy < Ho) & (ox < Wo);
         const long pix = inside ? ((long)it.img * Ho + oy) * Wo + ox : 0;
         float4 rr[4];
-        if (p.res && inside) {                                 // in flight while the MMAs of this tile finish
-          const float4 *r4 = reinterpret_cast<const float4 *>(p.res + pix * p.res_stride + n0);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) rr[g] = r4[g];
-        }
+        if (p.res && inside) lean_load_res(p.res + pix * p.res_stride + n0, p.res_wide != 0, rr);   // in flight while the MMAs finish
         mbar_wait(acc_full + as, phacc);
         tc_fence_after();
         epilogue_chunks_lean(p, tab, cpad, n_out, Npad, Cout, inside, pix, lane_base + as * (uint32_t)Npad, n0, rr);
@@ -1463,6 +1501,7 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
   p.res = a->res;
   p.res_stride = a->res_stride;
   if (a->res) KB_REQUIRE(a->res_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(a->res) & 15) == 0, "kb_conv2d: residual alignment");
+  p.res_wide = a->res && a->res_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(a->res) & 31) == 0 && !env_int("KB_CONV_NO_WIDE", 0);
   p.n_out = a->n_out;
   p.vec = (a->Cout % 4 == 0) && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0;
   for (int o = 0; o < a->n_out; ++o) {
@@ -1520,10 +1559,6 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
   p.a_stage_bytes = (box_bytes + 1023) & ~1023;
   p.acc_stages = min(kAccMax, 512 / npad);
   KB_REQUIRE(p.acc_stages >= 2, "kb_conv2d: accumulator does not fit TMEM");
-  // a team's first wait must be for the first phase of its accumulator stage: teams <= acc_stages
-  p.teams = p.fast ? max(1, min(min(env_int("KB_CONV_TEAMS", 3), 3), p.acc_stages)) : 0;
-  const int halo_threads = p.fast ? 64 + 128 * p.teams : kConvThreads;
-  p.tmem_cols = (uint32_t)max(32, pow2_at_least(p.acc_stages * npad));
   const size_t bar_bytes = 1024;                         // barriers + TMEM slot
   const size_t fixed = 1024 + bar_bytes + epi_bytes;     // alignment slack + barriers + epilogue tables
   const size_t budget = smem_cap - fixed;
@@ -1538,6 +1573,22 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
     KB_REQUIRE(p.b_stages >= 2, "kb_conv2d: weight ring does not fit shared memory");
   }
   if (a->stages > 0) p.a_stages = max(2, min(a->stages, p.a_stages));
+  // Two issuers halve the activation ring each of them sees: worth it only while a half still holds a whole tile plus one slot
+  // to load ahead into (measured: 64 -> 64 TF32 -- 2 chunks, 3 slots next to 144 KB of resident filters -- ran 146 us with two
+  // issuers on one slot each, 114 us with one issuer on three).
+  p.issuers = (p.resident && p.a_stages / 2 >= max(2, p.chunks) && !env_int("KB_CONV_ONE_ISSUER", 0)) ? kHaloIssuers : 1;
+  if (p.issuers == 2) {
+    // item i belongs to issuer i % 2, accumulator stage i % acc_stages and epilogue team i % 2: even ring sizes keep every
+    // barrier between ONE issuer and ONE team (or the producer), each visiting all of its phases in order
+    p.acc_stages &= ~1;
+    p.a_stages &= ~1;
+    p.teams = p.fast ? 2 : 0;
+  } else {
+    // a team's first wait must be for the first phase of its accumulator stage: teams <= acc_stages
+    p.teams = p.fast ? max(1, min(min(env_int("KB_CONV_TEAMS", 3), 3), p.acc_stages)) : 0;
+  }
+  p.tmem_cols = (uint32_t)max(32, pow2_at_least(p.acc_stages * npad));
+  const int halo_threads = p.fast ? 32 * kHaloEpiWarp0 + 128 * p.teams : kHaloThreads;
   KB_REQUIRE((2 * p.a_stages + 2 * p.b_stages + 2 * kAccMax) * sizeof(uint64_t) + 16 <= bar_bytes, "kb_conv2d: too many pipeline stages");
   p.epi_off = (int)((size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * b_bytes + bar_bytes);
   p.work_items = tiles * n_blocks;
