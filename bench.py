@@ -39,6 +39,14 @@ METRIC = "novel-view frames/sec at 1024x768, 150-frame KBE"
 DOLLY = False
 
 
+def _dtype_cnn():
+    """Operand type of the convolution stack in this process (KB200_CONV_F16=1 opts into fp16 operands)."""
+    from ken_burns_effect_b200.utils import convstack as cs
+    if cs.F16_ENABLED:
+        return "f16 operands in the GridNets / Refine (tcgen05 kind::f16, fp32 accumulate; KB200_CONV_F16=1), tf32 elsewhere"
+    return "tf32 (tcgen05 kind::tf32, fp32 accumulate)"
+
+
 def workload_name(frames):
     """config.workload, identical in both arms (the driver compares the strings)."""
     cfg = (2 if DOLLY else 1) if (W, H) == (1024, 768) else 3
@@ -125,7 +133,7 @@ def full_pipeline(steps=3, warmup=3, frames=150):
     total = t_cnn + t_render
     return {"value": frames * steps / total, "unit": "frames/s", "ms_per_kbe": 1e3 * total / steps,
             "ms_cnn_and_inpaint_stage": 1e3 * t_cnn / steps, "ms_render_loop": 1e3 * t_render / steps, "points": int(npts),
-            "conv_tflop_per_kbe": 2.30, "dtype_cnn": "tf32 (tcgen05 kind::tf32, fp32 accumulate; the render loop is f32)", "note": "random-init weights: the disparity is noise-like, so the appended point "
+            "conv_tflop_per_kbe": 2.30, "dtype_cnn": _dtype_cnn() + "; the render loop is f32", "note": "random-init weights: the disparity is noise-like, so the appended point "
             "count and hole statistics are not those of a trained model; CNN forwards replay from CUDA graphs from their 4th call on (captured during warm-up)"}
 
 
@@ -191,10 +199,10 @@ def throughput_mode(rank, world, dev, images_per_gpu=8, frames=150):
     ms_serial = _max_over_ranks(ms_serial, world, dev)
     n_img = images_per_gpu * world
     return {"what": f"configs[4]: {n_img} images of 1024x768, one {frames}-frame KBE each, {images_per_gpu} images per GPU, full pipeline "
-                    f"per rank (image in pinned host memory -> frames in pinned host memory), TF32 tcgen05 convolutions, depth stage in batches of {DEPTH_BATCH}",
+                    f"per rank (image in pinned host memory -> frames in pinned host memory), tcgen05 convolutions, depth stage in batches of {DEPTH_BATCH}",
             "images_per_s": n_img / (ms / 1e3), "frames_per_s": n_img * frames / (ms / 1e3), "ms_per_image_per_gpu": ms / images_per_gpu,
             "one_image_at_a_time": {"images_per_s": n_img / (ms_serial / 1e3), "ms_per_image_per_gpu": ms_serial / images_per_gpu},
-            "images": n_img, "dtype_cnn": "tf32", "weights": "random-init (no checkpoints offline)"}
+            "images": n_img, "dtype_cnn": _dtype_cnn(), "weights": "random-init (no checkpoints offline)"}
 
 
 def config3_4k(rank, world, dev, frames=300, steps=3, warmup=2):

@@ -1144,15 +1144,13 @@ __global__ void __launch_bounds__(256) k_pack_weights_f16(const float *__restric
 // (models/pointcloud_inpainting.py:70-72); output optionally cropped to (Ho, Wo) <= (2H, 2W).
 __global__ void __launch_bounds__(256) k_upsample2x_prelu(const float *__restrict__ x, long xs, int H, int W, int C4,
                                                           const float *__restrict__ slope, int C, float *__restrict__ y, long ys,
-                                                          int Ho, int Wo, int round, long total, const float *__restrict__ mul) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int cg = (int)(i % C4);
-  long r = i / C4;
-  const int ox = (int)(r % Wo);
-  r /= Wo;
-  const int oy = (int)(r % Ho);
-  const int n = (int)(r / Ho);
+                                                          int Ho, int Wo, int round, const float *__restrict__ mul) {
+  // grid: x over (output column, 4-channel group), y over (image, output row) -- 32-bit index arithmetic only (the flat 64-bit
+  // decomposition cost three emulated 64-bit divisions per thread, more instructions than the interpolation itself)
+  const unsigned ix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ix >= (unsigned)Wo * (unsigned)C4) return;
+  const int ox = (int)(ix / (unsigned)C4), cg = (int)(ix - (unsigned)ox * (unsigned)C4);
+  const int n = (int)(blockIdx.y / (unsigned)Ho), oy = (int)(blockIdx.y - (unsigned)n * (unsigned)Ho);
   // src = (dst + 0.5) / 2 - 0.5, clamped at 0 (PyTorch area_pixel_compute_source_index, align_corners=False)
   const float sx = fmaxf(__fmaf_rn((float)ox + 0.5f, 0.5f, -0.5f), 0.f), sy = fmaxf(__fmaf_rn((float)oy + 0.5f, 0.5f, -0.5f), 0.f);
   const int x0 = (int)sx, y0 = (int)sy;
@@ -1616,9 +1614,9 @@ int kb_upsample2x_prelu(const float *x, long x_stride, int N, int H, int W, int 
                  ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0,
              "kb_upsample2x_prelu: pointers must be 16-byte aligned, strides multiples of 16 bytes");
   const int C4 = (C + 3) / 4;
-  const long total = (long)N * Ho * Wo * C4;
-  k_upsample2x_prelu<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, x_stride, H, W, C4, slope, C, y, y_stride, Ho, Wo,
-                                                                        round_tf32, total, mul);
+  KB_REQUIRE((long)N * Ho <= 65535 && (long)Wo * C4 < (1L << 31), "kb_upsample2x_prelu: N * Ho must fit a grid dimension");
+  const dim3 grid((unsigned)cdiv((long)Wo * C4, 256), (unsigned)(N * Ho));
+  k_upsample2x_prelu<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_stride, H, W, C4, slope, C, y, y_stride, Ho, Wo, round_tf32, mul);
   count_launch();
   return check_launch("kb_upsample2x_prelu");
 }

@@ -68,8 +68,8 @@ def main():
     with open(out + "_summary.md", "w") as f:
         f.write(f"ncu --set full --clock-control none, per-launch averages; source: {rep}\n\n" + "\n".join(lines) + "\n")
     if "--traffic" in sys.argv:
-        # poses per launch of the captured command (bench.py scales the figure to its own launches): --poses K, default 32
-        traffic["_poses_per_launch"] = int(sys.argv[sys.argv.index("--poses") + 1]) if "--poses" in sys.argv else 32
+        # poses per launch of the captured command (bench.py scales the figure to its own launches): --poses K, default 30 (bench.py: 150 poses in 5 launches)
+        traffic["_poses_per_launch"] = int(sys.argv[sys.argv.index("--poses") + 1]) if "--poses" in sys.argv else 30
         traffic["_source"] = rep
         with open(out.rsplit("/", 1)[0] + "/ncu_traffic.json", "w") as f:
             json.dump(traffic, f, indent=1)
