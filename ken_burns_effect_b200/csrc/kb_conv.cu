@@ -191,8 +191,9 @@ constexpr int kABytes = kTileM * kChunk * 4;
 constexpr int kConvThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 // persistent kernel: warp 0 TMA, warps 1-2 MMA issuers, then the epilogue warps (8 with the generic epilogue, teams of 4 with the lean one)
 constexpr int kHaloIssuers = 2, kHaloEpiWarp0 = 1 + kHaloIssuers;
-constexpr int kHaloThreads = 32 * kHaloEpiWarp0 + 256;        // generic epilogue
-constexpr int kHaloMaxThreads = 32 * kHaloEpiWarp0 + 3 * 128;   // lean epilogue: up to three teams
+constexpr int kHaloThreads = 32 * kHaloEpiWarp0 + 256;        // generic epilogue: 8 warps on one tile
+constexpr int kHaloMaxTeams = 4;                               // lean epilogue: up to four teams of four warps
+constexpr int kHaloLeanThreads = 32 * kHaloEpiWarp0 + kHaloMaxTeams * 128;
 constexpr int kMaxOut = 3;
 
 struct ConvOut {
@@ -837,8 +838,10 @@ __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t A0, uint32_
   }
 }
 
-template <int KS, bool F16>
-__global__ void __launch_bounds__(kHaloMaxThreads, 1) k_conv_halo_tf32(const __grid_constant__ CUtensorMap map_a,
+// LEAN: the lean epilogue in teams of four warps (96 registers, up to 608 threads); otherwise the generic epilogue, 8 warps on one tile.
+// Two instantiations rather than a run-time branch: together the two epilogues need 121 registers, which caps the block at 512 threads.
+template <int KS, bool F16, bool LEAN>
+__global__ void __launch_bounds__(LEAN ? kHaloLeanThreads : kHaloThreads, 1) k_conv_halo_tf32(const __grid_constant__ CUtensorMap map_a,
                                                                     const __grid_constant__ CUtensorMap map_b,
                                                                     const ConvKernelParams p) {
   constexpr int kTaps = KS * KS;
@@ -867,7 +870,7 @@ __global__ void __launch_bounds__(kHaloMaxThreads, 1) k_conv_halo_tf32(const __g
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-    for (int s = 0; s < kAccMax; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, p.fast ? 4 : 8); }
+    for (int s = 0; s < kAccMax; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, LEAN ? 4 : 8); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -1047,7 +1050,7 @@ __global__ void __launch_bounds__(kHaloMaxThreads, 1) k_conv_halo_tf32(const __g
     const EpiSmem es = epi_stage(p, epi_tab, p.cpad, threadIdx.x - 32 * kHaloEpiWarp0, (int)blockDim.x - 32 * kHaloEpiWarp0);
     uint32_t as = 0, phacc = 0;
     TileIter it;
-    if (p.fast) {
+    if constexpr (LEAN) {
       // Teams of four warps (one per TMEM lane quadrant), team t on tiles t, t + teams, ...: the per-tile bookkeeping of a warp
       // (tile coordinates, pixel index, barrier wait) is paid once for all the chunks of its rows, and `teams` tiles are in
       // flight, which is what hides the latency of each warp's dependent chain (two or three warps per scheduler).
@@ -1074,20 +1077,19 @@ __global__ void __launch_bounds__(kHaloMaxThreads, 1) k_conv_halo_tf32(const __g
         while (as >= (uint32_t)acc_stages) { as -= acc_stages; phacc ^= 1u; }
       }
     } else {
-      it.init(p);
-    }
-    for (; it.left > 0; it.next(p)) {
-      const int n0 = it.nb * p.Npad;
-      const EpiPixel ep = epi_pixel(p, it.img, it.ty * kHaloTileH + py, it.tx * kHaloTileW + px);
-      float4 rr[4];
-      epi_load_res(p, ep, n0 + 16 * half, rr);                 // in flight while the MMAs of this tile finish
-      mbar_wait(acc_full + as, phacc);
-      tc_fence_after();
-      epilogue_rows(p, es, ep, tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.Npad, n0, half, rr);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
-      if (++as == (uint32_t)p.acc_stages) { as = 0; phacc ^= 1u; }
+      for (it.init(p); it.left > 0; it.next(p)) {
+        const int n0 = it.nb * p.Npad;
+        const EpiPixel ep = epi_pixel(p, it.img, it.ty * kHaloTileH + py, it.tx * kHaloTileW + px);
+        float4 rr[4];
+        epi_load_res(p, ep, n0 + 16 * half, rr);                 // in flight while the MMAs of this tile finish
+        mbar_wait(acc_full + as, phacc);
+        tc_fence_after();
+        epilogue_rows(p, es, ep, tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.Npad, n0, half, rr);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
+        if (++as == (uint32_t)p.acc_stages) { as = 0; phacc ^= 1u; }
+      }
     }
   }
   tc_fence_before();
@@ -1408,10 +1410,14 @@ static int raise_smem_limit() {
   const int big = 227 * 1024;
   cudaError_t e = cudaFuncSetAttribute(k_conv_tf32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_tf32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   if (e != cudaSuccess) {
     set_error("kb_conv2d: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     return (int)e;
@@ -1580,10 +1586,10 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
     // barrier between ONE issuer and ONE team (or the producer), each visiting all of its phases in order
     p.acc_stages &= ~1;
     p.a_stages &= ~1;
-    p.teams = p.fast ? 2 : 0;
+    p.teams = p.fast ? ((p.acc_stages >= 4 && env_int("KB_CONV_TEAMS", kHaloMaxTeams) >= 4) ? 4 : 2) : 0;
   } else {
     // a team's first wait must be for the first phase of its accumulator stage: teams <= acc_stages
-    p.teams = p.fast ? max(1, min(min(env_int("KB_CONV_TEAMS", 3), 3), p.acc_stages)) : 0;
+    p.teams = p.fast ? max(1, min(min(env_int("KB_CONV_TEAMS", kHaloMaxTeams), kHaloMaxTeams), p.acc_stages)) : 0;
   }
   p.tmem_cols = (uint32_t)max(32, pow2_at_least(p.acc_stages * npad));
   const int halo_threads = p.fast ? 32 * kHaloEpiWarp0 + 128 * p.teams : kHaloThreads;
@@ -1595,13 +1601,16 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
   const size_t smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * b_bytes + bar_bytes + epi_bytes;
   KB_REQUIRE(smem <= smem_cap, "kb_conv2d: pipeline does not fit shared memory");
   const unsigned grid = (unsigned)min((long)sm_count(), p.work_items);
+  const cudaStream_t st = (cudaStream_t)stream;
+#define KB_HALO_LAUNCH(KS_, F16_, LEAN_) k_conv_halo_tf32<KS_, F16_, LEAN_><<<grid, halo_threads, smem, st>>>(map_a, map_b, p)
   if (a->ksize == 1) {
-    if (p.f16) k_conv_halo_tf32<1, true><<<grid, halo_threads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
-    else k_conv_halo_tf32<1, false><<<grid, halo_threads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+    if (p.f16) { if (p.fast) KB_HALO_LAUNCH(1, true, true); else KB_HALO_LAUNCH(1, true, false); }
+    else { if (p.fast) KB_HALO_LAUNCH(1, false, true); else KB_HALO_LAUNCH(1, false, false); }
   } else {
-    if (p.f16) k_conv_halo_tf32<3, true><<<grid, halo_threads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
-    else k_conv_halo_tf32<3, false><<<grid, halo_threads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+    if (p.f16) { if (p.fast) KB_HALO_LAUNCH(3, true, true); else KB_HALO_LAUNCH(3, true, false); }
+    else { if (p.fast) KB_HALO_LAUNCH(3, false, true); else KB_HALO_LAUNCH(3, false, false); }
   }
+#undef KB_HALO_LAUNCH
   count_launch();
   return check_launch("kb_conv2d");
 }
