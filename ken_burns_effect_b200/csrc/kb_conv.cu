@@ -236,7 +236,7 @@ struct ConvKernelParams {
   int debug;            // KB_CONV_DEBUG bit mask (profiling experiments only, see the file header)
   int f16;              // operands are fp16 (activations and packed filters): kind::f16, 64 channels per 128-byte chunk
   int cpc;              // channels per chunk: 32 (tf32) or 64 (f16) -- a chunk is always one 128-byte swizzle row per pixel
-  int fast;             // lean epilogue (epilogue_chunks_lean): dense convolution, Cout % 16 == 0, no per-pixel factors, no debug bits
+  int fast;             // lean epilogue (epilogue_chunks_lean): Cout % 16 == 0, no debug bits that touch the epilogue
   int res_wide;         // every pixel of the residual starts on a 32-byte boundary
   int issuers;          // MMA-issuing warps: 2 with resident filters (items alternate; each issuer has its own half of the
                         // activation ring, its own accumulator stages and its own epilogue team), else 1
@@ -486,7 +486,7 @@ __device__ __forceinline__ int pin_reg(int v) { asm volatile("" : "+r"(v)); retu
 // chunk (loaded one chunk ahead), the residual of the next chunk (16 channels on) is requested into `nxt`.
 __device__ __forceinline__ void lean_chunk(const ConvKernelParams &p, uint32_t tab, int cpad, int n_out, bool inside, long pix,
                                            const float *res, uint32_t taddr, int c, bool more, const float4 (&cur)[4],
-                                           float4 (&nxt)[4]) {
+                                           float4 (&nxt)[4], bool pc, float ratio, float um) {
   uint32_t raw[16];
   tmem_ld16_issue(taddr, raw);
   if (more && res && inside) lean_load_res(res + c + 16, p.res_wide != 0, nxt);
@@ -502,6 +502,16 @@ __device__ __forceinline__ void lean_chunk(const ConvKernelParams &p, uint32_t t
     a[4 * g + 1] = __uint_as_float(raw[4 * g + 1]) + bs[g].y;
     a[4 * g + 2] = __uint_as_float(raw[4 * g + 2]) + bs[g].z;
     a[4 * g + 3] = __uint_as_float(raw[4 * g + 3]) + bs[g].w;
+  }
+  if (pc) {
+    // output = ((raw_out - bias) * mask_ratio + bias) * update_mask, utils/partial_conv.py:74-77, same operation order
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      a[4 * g] = __fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(a[4 * g], bs[g].x), ratio), bs[g].x), um);
+      a[4 * g + 1] = __fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(a[4 * g + 1], bs[g].y), ratio), bs[g].y), um);
+      a[4 * g + 2] = __fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(a[4 * g + 2], bs[g].z), ratio), bs[g].z), um);
+      a[4 * g + 3] = __fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(a[4 * g + 3], bs[g].w), ratio), bs[g].w), um);
+    }
   }
   if (res) {
 #pragma unroll
@@ -525,6 +535,17 @@ __device__ __forceinline__ void lean_chunk(const ConvKernelParams &p, uint32_t t
         w[4 * g] = prelu1(a[4 * g], sl.x); w[4 * g + 1] = prelu1(a[4 * g + 1], sl.y);
         w[4 * g + 2] = prelu1(a[4 * g + 2], sl.z); w[4 * g + 3] = prelu1(a[4 * g + 3], sl.w);
       }
+      if (out.mul) {
+        const float m = __ldg(out.mul + pix);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] *= m;
+      }
+      lean_store16(out, pix, c, w);
+    } else if (out.mul) {
+      const float m = __ldg(out.mul + pix);
+      float w[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = a[i] * m;
       lean_store16(out, pix, c, w);
     } else {
       lean_store16(out, pix, c, a);
@@ -537,17 +558,19 @@ __device__ __forceinline__ void lean_chunk(const ConvKernelParams &p, uint32_t t
 // instead of being copied.  `tab` is the shared-memory address of the epilogue tables (bias, then the slopes of output o at
 // (1 + o) * cpad floats); rr holds the residual of the first chunk.
 __device__ __forceinline__ void epilogue_chunks_lean(const ConvKernelParams &p, uint32_t tab, int cpad, int n_out, int Npad, int Cout,
-                                                     bool inside, long pix, uint32_t taddr, int n0, float4 (&rr)[4]) {
+                                                     bool inside, long pix, uint32_t taddr, int n0, float4 (&rr)[4], float ratio,
+                                                     float um) {
   const float *res = p.res ? p.res + pix * p.res_stride : nullptr;
+  const bool pc = p.pc_ratio != nullptr;
   float4 r2[4];
   int c0 = 0;
   for (;;) {
     bool more = (c0 + 16 < Npad) && (n0 + c0 + 16 < Cout);        // warp-uniform (Cout % 16 == 0: a chunk is whole or absent)
-    lean_chunk(p, tab, cpad, n_out, inside, pix, res, taddr + (uint32_t)c0, n0 + c0, more, rr, r2);
+    lean_chunk(p, tab, cpad, n_out, inside, pix, res, taddr + (uint32_t)c0, n0 + c0, more, rr, r2, pc, ratio, um);
     if (!more) break;
     c0 += 16;
     more = (c0 + 16 < Npad) && (n0 + c0 + 16 < Cout);
-    lean_chunk(p, tab, cpad, n_out, inside, pix, res, taddr + (uint32_t)c0, n0 + c0, more, r2, rr);
+    lean_chunk(p, tab, cpad, n_out, inside, pix, res, taddr + (uint32_t)c0, n0 + c0, more, r2, rr, pc, ratio, um);
     if (!more) break;
     c0 += 16;
   }
@@ -1067,9 +1090,11 @@ __global__ void __launch_bounds__(LEAN ? kHaloLeanThreads : kHaloThreads, 1) k_c
         const long pix = inside ? ((long)it.img * Ho + oy) * Wo + ox : 0;
         float4 rr[4];
         if (p.res && inside) lean_load_res(p.res + pix * p.res_stride + n0, p.res_wide != 0, rr);   // in flight while the MMAs finish
+        float ratio = 1.f, um = 1.f;                           // partial convolution: per-pixel mask_ratio and update_mask
+        if (p.pc_ratio) { ratio = __ldg(p.pc_ratio + pix); um = __ldg(p.pc_um + pix); }
         mbar_wait(acc_full + as, phacc);
         tc_fence_after();
-        epilogue_chunks_lean(p, tab, cpad, n_out, Npad, Cout, inside, pix, lane_base + as * (uint32_t)Npad, n0, rr);
+        epilogue_chunks_lean(p, tab, cpad, n_out, Npad, Cout, inside, pix, lane_base + as * (uint32_t)Npad, n0, rr, ratio, um);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
@@ -1556,9 +1581,7 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
   const int halo_w = kHaloTileW + a->ksize - 1, halo_h = kHaloTileH + a->ksize - 1;
   p.pitch = halo_w;
   p.debug = env_int("KB_CONV_DEBUG", 0);
-  p.fast = ((p.debug & ~6) == 0 && a->Cout % 16 == 0 && !a->pc_ratio && !env_int("KB_CONV_NO_LEAN", 0)) ? 1 : 0;
-  for (int o = 0; o < a->n_out; ++o)
-    if (a->out[o].mul) p.fast = 0;
+  p.fast = ((p.debug & ~6) == 0 && a->Cout % 16 == 0 && !env_int("KB_CONV_NO_LEAN", 0)) ? 1 : 0;
   const int box_bytes = p.pitch * halo_h * kChunk * 4;
   p.a_stage_bytes = (box_bytes + 1023) & ~1023;
   p.acc_stages = min(kAccMax, 512 / npad);
