@@ -236,7 +236,8 @@ struct ConvKernelParams {
   int debug;            // KB_CONV_DEBUG bit mask (profiling experiments only, see the file header)
   int f16;              // operands are fp16 (activations and packed filters): kind::f16, 64 channels per 128-byte chunk
   int cpc;              // channels per chunk: 32 (tf32) or 64 (f16) -- a chunk is always one 128-byte swizzle row per pixel
-  int fast;             // lean epilogue (epilogue_chunks_lean): Cout % 16 == 0, no debug bits that touch the epilogue
+  int fast;             // lean epilogue (Cout % 16 == 0, no debug bits that touch the epilogue): 1 dense, 2 with partial-conv
+                        // renormalisation / per-pixel output factors; 0 = generic epilogue
   int res_wide;         // every pixel of the residual starts on a 32-byte boundary
   int issuers;          // MMA-issuing warps: 2 with resident filters (items alternate; each issuer has its own half of the
                         // activation ring, its own accumulator stages and its own epilogue team), else 1
@@ -484,6 +485,9 @@ __device__ __forceinline__ int pin_reg(int v) { asm volatile("" : "+r"(v)); retu
 
 // One 16-column chunk of this thread's accumulator row: channels c .. c+15 of pixel `pix`.  `cur` holds the residual of this
 // chunk (loaded one chunk ahead), the residual of the next chunk (16 channels on) is requested into `nxt`.
+// PCMUL: the layer has a partial-convolution renormalisation and / or per-pixel output factors (compiled out of the dense form:
+// as run-time branches they cost the dense layers 2-3 % of a network forward -- registers, two spilled values, extra issue slots)
+template <bool PCMUL>
 __device__ __forceinline__ void lean_chunk(const ConvKernelParams &p, uint32_t tab, int cpad, int n_out, bool inside, long pix,
                                            const float *res, uint32_t taddr, int c, bool more, const float4 (&cur)[4],
                                            float4 (&nxt)[4], bool pc, float ratio, float um) {
@@ -503,7 +507,7 @@ __device__ __forceinline__ void lean_chunk(const ConvKernelParams &p, uint32_t t
     a[4 * g + 2] = __uint_as_float(raw[4 * g + 2]) + bs[g].z;
     a[4 * g + 3] = __uint_as_float(raw[4 * g + 3]) + bs[g].w;
   }
-  if (pc) {
+  if (PCMUL && pc) {
     // output = ((raw_out - bias) * mask_ratio + bias) * update_mask, utils/partial_conv.py:74-77, same operation order
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -535,13 +539,13 @@ __device__ __forceinline__ void lean_chunk(const ConvKernelParams &p, uint32_t t
         w[4 * g] = prelu1(a[4 * g], sl.x); w[4 * g + 1] = prelu1(a[4 * g + 1], sl.y);
         w[4 * g + 2] = prelu1(a[4 * g + 2], sl.z); w[4 * g + 3] = prelu1(a[4 * g + 3], sl.w);
       }
-      if (out.mul) {
+      if (PCMUL && out.mul) {
         const float m = __ldg(out.mul + pix);
 #pragma unroll
         for (int i = 0; i < 16; ++i) w[i] *= m;
       }
       lean_store16(out, pix, c, w);
-    } else if (out.mul) {
+    } else if (PCMUL && out.mul) {
       const float m = __ldg(out.mul + pix);
       float w[16];
 #pragma unroll
@@ -557,20 +561,21 @@ __device__ __forceinline__ void lean_chunk(const ConvKernelParams &p, uint32_t t
 // of four warps owns a tile, one warp per TMEM lane quadrant), two chunks per trip so that the residual buffers swap roles
 // instead of being copied.  `tab` is the shared-memory address of the epilogue tables (bias, then the slopes of output o at
 // (1 + o) * cpad floats); rr holds the residual of the first chunk.
+template <bool PCMUL>
 __device__ __forceinline__ void epilogue_chunks_lean(const ConvKernelParams &p, uint32_t tab, int cpad, int n_out, int Npad, int Cout,
                                                      bool inside, long pix, uint32_t taddr, int n0, float4 (&rr)[4], float ratio,
                                                      float um) {
   const float *res = p.res ? p.res + pix * p.res_stride : nullptr;
-  const bool pc = p.pc_ratio != nullptr;
+  const bool pc = PCMUL && p.pc_ratio != nullptr;
   float4 r2[4];
   int c0 = 0;
   for (;;) {
     bool more = (c0 + 16 < Npad) && (n0 + c0 + 16 < Cout);        // warp-uniform (Cout % 16 == 0: a chunk is whole or absent)
-    lean_chunk(p, tab, cpad, n_out, inside, pix, res, taddr + (uint32_t)c0, n0 + c0, more, rr, r2, pc, ratio, um);
+    lean_chunk<PCMUL>(p, tab, cpad, n_out, inside, pix, res, taddr + (uint32_t)c0, n0 + c0, more, rr, r2, pc, ratio, um);
     if (!more) break;
     c0 += 16;
     more = (c0 + 16 < Npad) && (n0 + c0 + 16 < Cout);
-    lean_chunk(p, tab, cpad, n_out, inside, pix, res, taddr + (uint32_t)c0, n0 + c0, more, r2, rr, pc, ratio, um);
+    lean_chunk<PCMUL>(p, tab, cpad, n_out, inside, pix, res, taddr + (uint32_t)c0, n0 + c0, more, r2, rr, pc, ratio, um);
     if (!more) break;
     c0 += 16;
   }
@@ -861,10 +866,11 @@ __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t A0, uint32_
   }
 }
 
-// LEAN: the lean epilogue in teams of four warps (96 registers, up to 608 threads); otherwise the generic epilogue, 8 warps on one tile.
-// Two instantiations rather than a run-time branch: together the two epilogues need 121 registers, which caps the block at 512 threads.
-template <int KS, bool F16, bool LEAN>
-__global__ void __launch_bounds__(LEAN ? kHaloLeanThreads : kHaloThreads, 1) k_conv_halo_tf32(const __grid_constant__ CUtensorMap map_a,
+// EPI 1 / 2: the lean epilogue in teams of four warps (96 registers, up to 608 threads), 2 = with partial-convolution renormalisation
+// and per-pixel output factors; EPI 0: the generic epilogue, 8 warps on one tile.  Instantiations rather than run-time branches:
+// together the epilogues need 121 registers, which caps the block at 512 threads.
+template <int KS, bool F16, int EPI>
+__global__ void __launch_bounds__(EPI ? kHaloLeanThreads : kHaloThreads, 1) k_conv_halo_tf32(const __grid_constant__ CUtensorMap map_a,
                                                                     const __grid_constant__ CUtensorMap map_b,
                                                                     const ConvKernelParams p) {
   constexpr int kTaps = KS * KS;
@@ -893,7 +899,7 @@ __global__ void __launch_bounds__(LEAN ? kHaloLeanThreads : kHaloThreads, 1) k_c
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-    for (int s = 0; s < kAccMax; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, LEAN ? 4 : 8); }
+    for (int s = 0; s < kAccMax; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, EPI ? 4 : 8); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -1073,7 +1079,7 @@ __global__ void __launch_bounds__(LEAN ? kHaloLeanThreads : kHaloThreads, 1) k_c
     const EpiSmem es = epi_stage(p, epi_tab, p.cpad, threadIdx.x - 32 * kHaloEpiWarp0, (int)blockDim.x - 32 * kHaloEpiWarp0);
     uint32_t as = 0, phacc = 0;
     TileIter it;
-    if constexpr (LEAN) {
+    if constexpr (EPI != 0) {
       // Teams of four warps (one per TMEM lane quadrant), team t on tiles t, t + teams, ...: the per-tile bookkeeping of a warp
       // (tile coordinates, pixel index, barrier wait) is paid once for all the chunks of its rows, and `teams` tiles are in
       // flight, which is what hides the latency of each warp's dependent chain (two or three warps per scheduler).
@@ -1091,10 +1097,10 @@ __global__ void __launch_bounds__(LEAN ? kHaloLeanThreads : kHaloThreads, 1) k_c
         float4 rr[4];
         if (p.res && inside) lean_load_res(p.res + pix * p.res_stride + n0, p.res_wide != 0, rr);   // in flight while the MMAs finish
         float ratio = 1.f, um = 1.f;                           // partial convolution: per-pixel mask_ratio and update_mask
-        if (p.pc_ratio) { ratio = __ldg(p.pc_ratio + pix); um = __ldg(p.pc_um + pix); }
+        if (EPI == 2 && p.pc_ratio) { ratio = __ldg(p.pc_ratio + pix); um = __ldg(p.pc_um + pix); }
         mbar_wait(acc_full + as, phacc);
         tc_fence_after();
-        epilogue_chunks_lean(p, tab, cpad, n_out, Npad, Cout, inside, pix, lane_base + as * (uint32_t)Npad, n0, rr, ratio, um);
+        epilogue_chunks_lean<EPI == 2>(p, tab, cpad, n_out, Npad, Cout, inside, pix, lane_base + as * (uint32_t)Npad, n0, rr, ratio, um);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
@@ -1435,14 +1441,18 @@ static int raise_smem_limit() {
   const int big = 227 * 1024;
   cudaError_t e = cudaFuncSetAttribute(k_conv_tf32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_tf32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<1, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<3, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<3, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<3, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<3, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<3, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo_tf32<3, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   if (e != cudaSuccess) {
     set_error("kb_conv2d: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     return (int)e;
@@ -1582,6 +1592,9 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
   p.pitch = halo_w;
   p.debug = env_int("KB_CONV_DEBUG", 0);
   p.fast = ((p.debug & ~6) == 0 && a->Cout % 16 == 0 && !env_int("KB_CONV_NO_LEAN", 0)) ? 1 : 0;
+  if (p.fast && a->pc_ratio) p.fast = 2;
+  for (int o = 0; o < a->n_out; ++o)
+    if (p.fast && a->out[o].mul) p.fast = 2;
   const int box_bytes = p.pitch * halo_h * kChunk * 4;
   p.a_stage_bytes = (box_bytes + 1023) & ~1023;
   p.acc_stages = min(kAccMax, 512 / npad);
@@ -1625,14 +1638,19 @@ int kb_conv2d(const kb_conv_args *a, kb_stream_t stream) {
   KB_REQUIRE(smem <= smem_cap, "kb_conv2d: pipeline does not fit shared memory");
   const unsigned grid = (unsigned)min((long)sm_count(), p.work_items);
   const cudaStream_t st = (cudaStream_t)stream;
-#define KB_HALO_LAUNCH(KS_, F16_, LEAN_) k_conv_halo_tf32<KS_, F16_, LEAN_><<<grid, halo_threads, smem, st>>>(map_a, map_b, p)
+#define KB_HALO_LAUNCH(KS_, F16_, EPI_) k_conv_halo_tf32<KS_, F16_, EPI_><<<grid, halo_threads, smem, st>>>(map_a, map_b, p)
+#define KB_HALO_EPI(KS_, F16_)                         \
+  do {                                                 \
+    if (p.fast == 2) KB_HALO_LAUNCH(KS_, F16_, 2);     \
+    else if (p.fast == 1) KB_HALO_LAUNCH(KS_, F16_, 1); \
+    else KB_HALO_LAUNCH(KS_, F16_, 0);                 \
+  } while (0)
   if (a->ksize == 1) {
-    if (p.f16) { if (p.fast) KB_HALO_LAUNCH(1, true, true); else KB_HALO_LAUNCH(1, true, false); }
-    else { if (p.fast) KB_HALO_LAUNCH(1, false, true); else KB_HALO_LAUNCH(1, false, false); }
+    if (p.f16) KB_HALO_EPI(1, true); else KB_HALO_EPI(1, false);
   } else {
-    if (p.f16) { if (p.fast) KB_HALO_LAUNCH(3, true, true); else KB_HALO_LAUNCH(3, true, false); }
-    else { if (p.fast) KB_HALO_LAUNCH(3, false, true); else KB_HALO_LAUNCH(3, false, false); }
+    if (p.f16) KB_HALO_EPI(3, true); else KB_HALO_EPI(3, false);
   }
+#undef KB_HALO_EPI
 #undef KB_HALO_LAUNCH
   count_launch();
   return check_launch("kb_conv2d");
