@@ -1178,38 +1178,59 @@ __global__ void __launch_bounds__(256) k_pack_weights_f16(const float *__restric
 __global__ void __launch_bounds__(256) k_upsample2x_prelu(const float *__restrict__ x, long xs, int H, int W, int C4,
                                                           const float *__restrict__ slope, int C, float *__restrict__ y, long ys,
                                                           int Ho, int Wo, int round, const float *__restrict__ mul) {
-  // grid: x over (output column, 4-channel group), y over (image, output row) -- 32-bit index arithmetic only (the flat 64-bit
-  // decomposition cost three emulated 64-bit divisions per thread, more instructions than the interpolation itself)
-  const unsigned ix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ix >= (unsigned)Wo * (unsigned)C4) return;
-  const int ox = (int)(ix / (unsigned)C4), cg = (int)(ix - (unsigned)ox * (unsigned)C4);
-  const int n = (int)(blockIdx.y / (unsigned)Ho), oy = (int)(blockIdx.y - (unsigned)n * (unsigned)Ho);
-  // src = (dst + 0.5) / 2 - 0.5, clamped at 0 (PyTorch area_pixel_compute_source_index, align_corners=False)
-  const float sx = fmaxf(__fmaf_rn((float)ox + 0.5f, 0.5f, -0.5f), 0.f), sy = fmaxf(__fmaf_rn((float)oy + 0.5f, 0.5f, -0.5f), 0.f);
-  const int x0 = (int)sx, y0 = (int)sy;
-  const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
-  const float lx = sx - (float)x0, ly = sy - (float)y0;
-  const float hx = 1.f - lx, hy = 1.f - ly;
+  // One thread per (input cell, 4-channel group): the cell between input pixels (ix, ix + 1) x (iy, iy + 1), ix = -1 .. W - 1,
+  // holds the 2 x 2 output pixels (2 ix + 1, 2 ix + 2) x (2 iy + 1, 2 iy + 2), all interpolated from those four inputs:
+  //   src = (dst + 0.5) / 2 - 0.5, clamped at 0 (PyTorch area_pixel_compute_source_index, align_corners=False)
+  //   dst = 2 i + 1 -> src = i + 0.25;  dst = 2 i + 2 -> src = i + 0.75;  dst = 0 -> src = 0 (cell -1, weight 1 on pixel 0).
+  // Four 16-byte loads feed four outputs (the one-output-per-thread form loaded four per output and was bound by its own
+  // instruction stream).  grid: x over (cell column, channel group), y over (image, cell row): 32-bit index arithmetic only.
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (unsigned)(W + 1) * (unsigned)C4) return;
+  const int cx = (int)(t / (unsigned)C4), cg = (int)(t - (unsigned)cx * (unsigned)C4);
+  const int n = (int)(blockIdx.y / (unsigned)(H + 1)), cy = (int)(blockIdx.y - (unsigned)n * (unsigned)(H + 1));
+  const int ix = cx - 1, iy = cy - 1;
+  const int x0 = max(ix, 0), x1 = min(ix + 1, W - 1), y0 = max(iy, 0), y1 = min(iy + 1, H - 1);
   const float *b = x + (long)n * H * W * xs + 4 * cg;
   const float4 p00 = *reinterpret_cast<const float4 *>(b + ((long)y0 * W + x0) * xs);
   const float4 p01 = *reinterpret_cast<const float4 *>(b + ((long)y0 * W + x1) * xs);
   const float4 p10 = *reinterpret_cast<const float4 *>(b + ((long)y1 * W + x0) * xs);
   const float4 p11 = *reinterpret_cast<const float4 *>(b + ((long)y1 * W + x1) * xs);
-  float o[4];
   const float a00[4] = {p00.x, p00.y, p00.z, p00.w}, a01[4] = {p01.x, p01.y, p01.z, p01.w};
   const float a10[4] = {p10.x, p10.y, p10.z, p10.w}, a11[4] = {p11.x, p11.y, p11.z, p11.w};
+  float sl[4] = {1.f, 1.f, 1.f, 1.f};
+  if (slope) {
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    // same association as ATen's upsample_bilinear2d: hy*(hx*p00 + lx*p01) + ly*(hx*p10 + lx*p11)
-    float v = hy * (hx * a00[e] + lx * a01[e]) + ly * (hx * a10[e] + lx * a11[e]);
-    const int c = 4 * cg + e;
-    if (slope && c < C) v = v > 0.f ? v : v * __ldg(slope + c);
-    if (c >= C) v = 0.f;
-    if (mul) v *= __ldg(mul + ((long)n * Ho + oy) * Wo + ox);
-    o[e] = round == 1 ? round_tf32(v) : v;
+    for (int e = 0; e < 4; ++e)
+      if (4 * cg + e < C) sl[e] = __ldg(slope + 4 * cg + e);
   }
-  if (round == 2) store_half4(y, (((long)n * Ho + oy) * Wo + ox) * ys + 4 * cg, make_float4(o[0], o[1], o[2], o[3]));   // fp16 output
-  else *reinterpret_cast<float4 *>(y + (((long)n * Ho + oy) * Wo + ox) * ys + 4 * cg) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+    const int oy = 2 * iy + 1 + dy;
+    if (oy < 0 || oy >= Ho) continue;
+    // weight of the lower row: 0.25 / 0.75, and 0 for output row 0 (clamped source)
+    const float ly = dy == 0 ? 0.25f : (iy < 0 ? 0.f : 0.75f), hy = 1.f - ly;
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int ox = 2 * ix + 1 + dx;
+      if (ox < 0 || ox >= Wo) continue;
+      const float lx = dx == 0 ? 0.25f : (ix < 0 ? 0.f : 0.75f), hx = 1.f - lx;
+      const long opix = ((long)n * Ho + oy) * Wo + ox;
+      const float m = mul ? __ldg(mul + opix) : 1.f;
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        // same association as ATen's upsample_bilinear2d: hy*(hx*p00 + lx*p01) + ly*(hx*p10 + lx*p11)
+        float v = hy * (hx * a00[e] + lx * a01[e]) + ly * (hx * a10[e] + lx * a11[e]);
+        const int c = 4 * cg + e;
+        if (slope && c < C) v = v > 0.f ? v : v * sl[e];
+        if (c >= C) v = 0.f;
+        if (mul) v *= m;
+        o[e] = round == 1 ? round_tf32(v) : v;
+      }
+      if (round == 2) store_half4(y, opix * ys + 4 * cg, make_float4(o[0], o[1], o[2], o[3]));   // fp16 output
+      else *reinterpret_cast<float4 *>(y + opix * ys + 4 * cg) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
 }
 
 // y = prelu(x) (slope per channel; nullptr = copy), NHWC with independent pixel strides.
@@ -1664,8 +1685,8 @@ int kb_upsample2x_prelu(const float *x, long x_stride, int N, int H, int W, int 
                  ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0,
              "kb_upsample2x_prelu: pointers must be 16-byte aligned, strides multiples of 16 bytes");
   const int C4 = (C + 3) / 4;
-  KB_REQUIRE((long)N * Ho <= 65535 && (long)Wo * C4 < (1L << 31), "kb_upsample2x_prelu: N * Ho must fit a grid dimension");
-  const dim3 grid((unsigned)cdiv((long)Wo * C4, 256), (unsigned)(N * Ho));
+  KB_REQUIRE((long)N * (H + 1) <= 65535 && (long)(W + 1) * C4 < (1L << 31), "kb_upsample2x_prelu: N * (H + 1) must fit a grid dimension");
+  const dim3 grid((unsigned)cdiv((long)(W + 1) * C4, 256), (unsigned)(N * (H + 1)));
   k_upsample2x_prelu<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_stride, H, W, C4, slope, C, y, y_stride, Ho, Wo, round_tf32, mul);
   count_launch();
   return check_launch("kb_upsample2x_prelu");
