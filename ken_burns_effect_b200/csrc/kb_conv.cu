@@ -15,16 +15,22 @@
 //   * weights are pre-packed per (tap, 32-channel slice) as K-major [Cout][32] panels, TMA-loaded next to A.
 //   * both operands land in shared memory in the 128-byte swizzled K-major layout that tcgen05.mma reads
 //     through shared-memory descriptors; the accumulator (128 lanes x Npad fp32 columns) lives in TMEM.
-//   * warp 0 = TMA producer, warp 1 = MMA issuer (both run their loops as whole warps, one elected lane issues),
-//     warps 2..9 = epilogue: tcgen05.ld the accumulator, + bias, partial-conv renormalisation, + residual, then up to
+//   * warp 0 = TMA producer, then the MMA issuer(s) (all run their loops as whole warps, one elected lane issues),
+//     then the epilogue warps: tcgen05.ld the accumulator, + bias, partial-conv renormalisation, + residual, then up to
 //     three outputs, each optionally passed through the next layer's PReLU and the consumer's mask, so that
 //     "PReLU -> conv" chains never need a separate elementwise pass.
 //   * a ring of `stages` shared-memory slots with full/empty mbarriers decouples TMA from the tensor pipe.
-// Two kernels: k_conv_tf32 (one TMA load per filter tap, any filter; two CTAs per SM so that one CTA's epilogue overlaps
-// the other's main loop) and the persistent k_conv_halo_tf32 (stride 1, k <= 3: one halo load per tile, taps are
-// descriptor offsets, resident filters, accumulator ring in TMEM) -- see the comment above it.
-// KB_CONV_DEBUG (bit mask, profiling experiments only -- results are WRONG with any bit set): 1 no epilogue stores,
-// 2 no MMAs, 4 no activation loads, 8 no TMEM reads; this is how DESIGN.md's "what bounds the kernel" numbers were taken.
+//   * operands are TF32 (fp32 tensors) or, per call, fp16 (kb_conv_args.x_f16: fp16 activations, fp16 filter panels, 64
+//     channels per 128-byte chunk, kind::f16); accumulation, bias, residual and fp32 outputs are the same in both.
+// Two kernels: k_conv_tf32 (one TMA load per filter tap, any filter; warps 0 / 1 / 2-9; two CTAs per SM so that one CTA's
+// epilogue overlaps the other's main loop) and the persistent k_conv_halo_tf32 (stride 1, k <= 3: one halo load per tile, taps
+// are descriptor offsets, resident filters, accumulator ring in TMEM, two MMA issuers, epilogue in teams of four warps) --
+// see the comment above it.
+// Environment switches (experiments; the defaults are what the measurements in DESIGN.md section 5 chose):
+//   KB_CONV_DEBUG   bit mask, results are WRONG with any bit set: 1 no epilogue stores, 2 no MMAs, 4 no activation loads,
+//                   8 no TMEM reads (1 and 8 select the generic epilogue) -- how "what bounds the kernel" was measured
+//   KB_CONV_NO_LEAN=1 generic epilogue everywhere   KB_CONV_TEAMS=n epilogue teams (<= 4)   KB_CONV_ONE_ISSUER=1
+//   KB_CONV_NO_WIDE=1 16-byte instead of 32-byte global loads / stores   KB_CONV_NO_RESIDENT=1   KB_CONV_ALGO=1|2
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
