@@ -600,7 +600,10 @@ def main():
                    "l2": "no explicit flush: each step streams ~0.8 GB of z-buffers/accumulators/frames (> 126 MB L2)"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(packed_host.numel() * 4) if rank == 0 else 0,
-                "d2h_bytes_per_step": int(frames_host.numel())},
+                "d2h_bytes_per_step": int(frames_host.numel()),
+                "overlap": ("the cloud of step i+1 is uploaded (own stream, second device buffer) while the frames of step i copy out; "
+                            "every step moves its own cloud in and its own frames out" if world == 1 else
+                            "rank 0 uploads the cloud, then the NCCL broadcast, then every rank's frames copy out")},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
